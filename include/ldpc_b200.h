@@ -1,0 +1,169 @@
+/*
+ * ldpc_b200.h -- C ABI of the B200-native LDPC flood decoder (libldpc_b200.so).
+ *
+ * This is the drop-in boundary for the reference's decoder class
+ *   h/ldpc_decoder_gpu.h:15-139  (CUDA twin h/ldpc_decoder_gpu_cuda.h:11-145)
+ * of kunzjacq/ldpc_decoder.  The reference has no FFI layer of its own; the
+ * header-compatible C++14 class in ldpc_decoder_b200/csrc/ldpc_decoder_gpu.h
+ * forwards to these entry points.
+ *
+ * Plain pointers and sizes only; no exceptions cross this boundary: every
+ * function returns an ldpc_b200_status and ldpc_b200_last_error() gives text.
+ * There is no CPU fallback: without a CUDA device every call that needs one
+ * returns LDPC_B200_ERR_CUDA.
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ldpc_b200_status {
+  LDPC_B200_OK = 0,
+  LDPC_B200_ERR_INVALID = 1,     /* bad argument                                              */
+  LDPC_B200_ERR_CODE = 2,        /* "Incorrect code structure" (ldpc_decoder_gpu.cu:40-58)    */
+  LDPC_B200_ERR_MULTIPLE_32 = 3, /* N % 32 != 0 (ldpc_decoder_gpu.cu:30-32)                   */
+  LDPC_B200_ERR_CUDA = 4,        /* CUDA runtime failure / no device                          */
+  LDPC_B200_ERR_NOMEM = 5,       /* does not fit in device memory                             */
+  LDPC_B200_ERR_IO = 6,          /* alist file could not be opened (ldpc_code.cpp:26-29)      */
+  LDPC_B200_ERR_ALIST = 7        /* malformed alist (ldpc_code.cpp:114-117)                   */
+} ldpc_b200_status;
+
+typedef enum ldpc_b200_precision {
+  LDPC_B200_FP32 = 0, /* llr_t = float  (reference built without USE_FLOAT16_COMPUTE) */
+  LDPC_B200_FP16 = 1  /* llr_t = __half (reference CMake default, common.h:17-19)     */
+} ldpc_b200_precision;
+
+typedef enum ldpc_b200_channel {
+  LDPC_B200_AWGN = 0, /* llr = x * param,            param = 2/sigma^2  (flood.cu:62-75, channel.h:70-73) */
+  LDPC_B200_BSC = 1,  /* llr = copysign(param, x),   param = ln((1-p)/p) (flood.cu:47-60, channel.cpp:6-9) */
+  LDPC_B200_LLR = 2   /* input already holds LLRs (decoding_input_is_llr() == true path)                  */
+} ldpc_b200_channel;
+
+/* ---- code graph (replaces ldpc_code, h/ldpc_code.h:10-54) ---------------------------- */
+typedef struct ldpc_b200_code ldpc_b200_code;
+
+/* Parse the reference's alist dialect (src/ldpc_code.cpp:45-152). */
+ldpc_b200_status ldpc_b200_code_load_alist(const char *path, ldpc_b200_code **out);
+ldpc_b200_status ldpc_b200_code_parse_alist(const char *text, size_t len, ldpc_b200_code **out);
+/* Build from CSR arrays: row_ptr[M+1], col_idx[E] = variable of each check-major edge. */
+ldpc_b200_status ldpc_b200_code_from_csr(uint32_t n_checks, uint32_t n_vars, const uint32_t *row_ptr,
+                                         const uint32_t *col_idx, uint32_t n_erased_vars, ldpc_b200_code **out);
+void ldpc_b200_code_destroy(ldpc_b200_code *code);
+
+typedef struct ldpc_b200_code_info {
+  uint32_t n_checks, n_vars, n_edges, n_erased_vars, n_erased_checks;
+  uint32_t max_deg_var, max_deg_check;
+  const uint32_t *row_ptr;         /* [M+1] out_bit_to_edge  (check-major CSR offsets)  */
+  const uint32_t *col_ptr;         /* [N+1] in_bit_to_edge   (variable-major offsets)   */
+  const uint32_t *in_to_out;       /* [E]   edge_in_to_out                              */
+  const uint32_t *out_to_in;       /* [E]   edge_out_to_in                              */
+  const uint32_t *out_edge_to_var; /* [E]   variable of each check-major edge           */
+} ldpc_b200_code_info;
+ldpc_b200_status ldpc_b200_code_get_info(const ldpc_b200_code *code, ldpc_b200_code_info *info);
+void ldpc_b200_code_set_erased_vars(ldpc_b200_code *code, uint32_t n_erased); /* ldpc_code.cpp:164-167 */
+
+/* ---- decoder (replaces ldpc_decoder_gpu / ldpc_decoder_gpu_cuda) ------------------- */
+typedef struct ldpc_b200_decoder ldpc_b200_decoder;
+
+typedef struct ldpc_b200_config {
+  int32_t precision;            /* ldpc_b200_precision                                            */
+  uint32_t max_log2_frames;     /* m_max_log_parallel_factor_user (ldpc_decoder_gpu_common.h:13)  */
+  int32_t device;               /* CUDA device ordinal; -1 = current device                       */
+  uint32_t mem_headroom_pct;    /* device memory left unused; 0 -> 10 (ldpc_decoder_gpu.cu:85)    */
+  uint32_t reserved[4];
+} ldpc_b200_config;
+
+/* Constructor: validates the graph, sizes frames-in-flight P = min(2^floor(log2 fit), 2^max_log2_frames)
+ * from free device memory (ldpc_decoder_gpu.cu:67-99), allocates and uploads. */
+ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code, const ldpc_b200_config *cfg,
+                                          ldpc_b200_decoder **out);
+void ldpc_b200_decoder_destroy(ldpc_b200_decoder *dec);
+/* parallel_factor() (ldpc_decoder_gpu.h:120-123) */
+uint32_t ldpc_b200_decoder_frames_in_flight(const ldpc_b200_decoder *dec);
+/* set_erased_variables() (ldpc_decoder_gpu.h:125-128) */
+void ldpc_b200_decoder_set_erased_vars(ldpc_b200_decoder *dec, uint32_t n_erased);
+
+enum {
+  LDPC_B200_LAYOUT_INTERLEAVED = 0, /* element [v + n_frames*i] (reference API, ldpc_decoder_gpu.h:93-94) */
+  LDPC_B200_LAYOUT_FRAME_MAJOR = 1  /* element [v*frame_stride + i] (extension)         */
+};
+
+typedef struct ldpc_b200_decode_params {
+  int32_t channel;                /* ldpc_b200_channel                                                */
+  float channel_param;            /* ref_llr() or factor()                                            */
+  uint32_t num_iter_max;          /* m_num_iter_max          (default 100)                            */
+  uint32_t num_iter_check_parity; /* m_num_iter_check_parity (default 10)                             */
+  int32_t input_layout;           /* LDPC_B200_LAYOUT_*                                               */
+  uint64_t frame_stride;          /* FRAME_MAJOR: elements between frames; 0 -> N - n_erased          */
+  uint32_t input_pool_frames;     /* 0: input holds n_frames frames.  k>0: input/syndromes hold k      *
+                                   * frames and frame f reads column f % k (benchmark recycling pool)  */
+  uint32_t flags;                 /* LDPC_B200_FLAG_*                                                  */
+  uint32_t reserved[4];
+} ldpc_b200_decode_params;
+
+enum {
+  LDPC_B200_FLAG_SIMD_PAIRS = 1u /* refill counts rounded down to even, as the reference's OpenCL *
+                                  * backend does (ldpc_decoder_gpu.cpp:623)                       */
+};
+
+typedef struct ldpc_b200_report {
+  uint32_t max_iter, min_iter; /* test_report fields written by decode (ldpc_decoder_gpu.cu:616-628) */
+  float avg_iter;
+  float iter_time_per_vector;
+  uint32_t global_iters;       /* flood iterations executed                                  */
+  uint32_t n_checks_run;       /* syndrome checks executed                                   */
+  double elapsed_s;            /* wall time of the call                                      */
+  double device_s;             /* CUDA-event time first kernel -> last result                */
+  double cn_s, vn_s;           /* accumulated CUDA-event time of the CN / VN kernels         */
+  uint64_t cn_launches, vn_launches, other_launches;
+  uint64_t h2d_bytes, d2h_bytes;
+} ldpc_b200_report;
+
+/* decode() (ldpc_decoder_gpu.h:102-110; semantics of ldpc_decoder_gpu.cu:283-634).
+ * input     : channel values, llr_t elements (float, or IEEE half bits when FP16); host or device pointer.
+ * syndromes : u32[n_frames * ceil(M/32)] frame-major, bit i of word w = check 32w+i; host or device.
+ * results   : u32[n_frames * N/32] frame-major, LSB-first; host or device.
+ * iter_counts (nullable): per-frame iter_end - iter_start; host.
+ * n_frames == 0 returns immediately (ldpc_decoder_gpu.cu:293-294). */
+ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *dec, const ldpc_b200_decode_params *params, uint32_t n_frames,
+                                  const void *input, const uint32_t *syndromes, uint32_t *results,
+                                  ldpc_b200_report *report, uint32_t *iter_counts);
+
+/* ---- kernel-level entry points (parity tests and profiling; same kernels decode() runs) ------ */
+/* Load cnt <= P frames into slots [0,cnt): staged[j + cnt*i] channel values (ldpc_decoder_gpu.cu:218-273). */
+ldpc_b200_status ldpc_b200_debug_refill(ldpc_b200_decoder *dec, int32_t channel, float channel_param, uint32_t cnt,
+                                        const void *staged, const uint32_t *syndromes);
+/* n flood iterations (check-node pass then variable-node pass); the last variable-node pass also emits hard
+ * decisions when final_bits != 0.  Optionally returns the accumulated CUDA-event time of each pass. */
+ldpc_b200_status ldpc_b200_debug_iterate(ldpc_b200_decoder *dec, uint32_t n_iters, int32_t final_bits,
+                                         float *cn_ms, float *vn_ms);
+/* one check-node / variable-node pass only */
+ldpc_b200_status ldpc_b200_debug_cn_pass(ldpc_b200_decoder *dec);
+ldpc_b200_status ldpc_b200_debug_vn_pass(ldpc_b200_decoder *dec, int32_t final_bits);
+/* syndrome check on the current hard decisions: violated[P] bytes (flood.cu:191-223) */
+ldpc_b200_status ldpc_b200_debug_check(ldpc_b200_decoder *dec, uint8_t *violated);
+/* messages of one slot in check-major edge order, widened to float; priors likewise */
+ldpc_b200_status ldpc_b200_debug_read_messages(ldpc_b200_decoder *dec, uint32_t slot, float *out_e);
+ldpc_b200_status ldpc_b200_debug_read_priors(ldpc_b200_decoder *dec, uint32_t slot, float *out_n);
+/* packed hard decisions of one slot, u32[N/32] LSB-first (flood.cu:277-295) */
+ldpc_b200_status ldpc_b200_debug_read_hard(ldpc_b200_decoder *dec, uint32_t slot, uint32_t *out_words);
+/* the 32768-entry fp16 phi_abs table the FP16 kernels use (index = |x| half bits) */
+ldpc_b200_status ldpc_b200_phi_table_fp16(ldpc_b200_decoder *dec, uint16_t *table);
+/* element-wise phi_abs on the device, fp32 path (flood.cu:31-37) */
+ldpc_b200_status ldpc_b200_debug_phi_abs_f32(const float *x, float *y, size_t n);
+
+/* algorithmic bytes of one flood iteration of ONE frame: (4E+N)*s + 4*ceil(M/32) */
+uint64_t ldpc_b200_bytes_per_frame_iteration(const ldpc_b200_decoder *dec);
+
+const char *ldpc_b200_last_error(void);
+const char *ldpc_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */

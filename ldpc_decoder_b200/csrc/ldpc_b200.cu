@@ -1,0 +1,854 @@
+// ldpc_b200.cu -- C ABI (include/ldpc_b200.h) and host scheduler of the B200 flood decoder.
+//
+// Replaces, for the decode hot path, the reference's
+//   src/ldpc_decoder_gpu.cu:20-634 (constructor, prepare_vectors, transfer_vectors, decode)
+//   h/cuda_manager.h + src/cuda/cuda_manager.cpp (runtime wrapper)
+// with: 64-bit-indexed [E][P] message arrays, slot indirection instead of flood_permute_vecs,
+// bit-sliced syndromes / hard decisions, and refills written straight into freed slots.
+#include "../../include/ldpc_b200.h"
+
+#include "ldpc_code.h"
+#include "ldpc_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace ldpc_b200;
+
+// ------------------------------------------------------------------ error plumbing
+namespace {
+
+thread_local std::string g_last_error;
+
+ldpc_b200_status fail(ldpc_b200_status st, const std::string &msg) {
+  g_last_error = msg;
+  return st;
+}
+
+#define CU_TRY(expr)                                                                                                   \
+  do {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess)                                                                                             \
+      return fail(LDPC_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+  } while (0)
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T> struct dev_buf { // RAII device allocation
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    return cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+  ~dev_buf() { release(); }
+};
+
+template <typename T> struct pinned_buf { // RAII pinned host allocation
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    return cudaMallocHost(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+  }
+  ~pinned_buf() { release(); }
+};
+
+bool is_device_pointer(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+uint32_t ilog2(uint64_t x) {
+  uint32_t r = 0;
+  while ((uint64_t(1) << (r + 1)) <= x) ++r;
+  return r;
+}
+
+// host worker threads for the strided gather (prepare_vectors, ldpc_decoder_gpu.cu:199-207)
+void parallel_for(size_t n, unsigned n_threads, const std::function<void(size_t, size_t)> &fn) {
+  n_threads = std::max(1u, std::min<unsigned>(n_threads, unsigned((n + 4095) / 4096)));
+  if (n_threads == 1) {
+    fn(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t chunk = (n + n_threads - 1) / n_threads;
+  for (unsigned t = 0; t < n_threads; ++t) {
+    const size_t a = std::min(n, t * chunk), b = std::min(n, a + chunk);
+    if (a < b) th.emplace_back(fn, a, b);
+  }
+  for (auto &t : th) t.join();
+}
+} // namespace
+
+// ------------------------------------------------------------------ code object
+struct ldpc_b200_code {
+  std::unique_ptr<ldpc_code> code;
+};
+
+extern "C" {
+
+const char *ldpc_b200_last_error(void) { return g_last_error.c_str(); }
+const char *ldpc_b200_version(void) { return "ldpc_b200 0.1 (sm_100a)"; }
+
+static ldpc_b200_status wrap_code(std::function<ldpc_code *()> make, ldpc_b200_code **out) {
+  if (!out) return fail(LDPC_B200_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  try {
+    std::unique_ptr<ldpc_code> c(make());
+    *out = new ldpc_b200_code{std::move(c)};
+    return LDPC_B200_OK;
+  } catch (const error &e) {
+    const std::string msg = e.what();
+    return fail(msg.find("could not be opened") != std::string::npos ? LDPC_B200_ERR_IO : LDPC_B200_ERR_ALIST, msg);
+  } catch (const std::exception &e) {
+    return fail(LDPC_B200_ERR_INVALID, e.what());
+  }
+}
+
+ldpc_b200_status ldpc_b200_code_load_alist(const char *path, ldpc_b200_code **out) {
+  if (!path) return fail(LDPC_B200_ERR_INVALID, "null path");
+  return wrap_code([&] { return new ldpc_code(std::string(path), true); }, out);
+}
+
+ldpc_b200_status ldpc_b200_code_parse_alist(const char *text, size_t len, ldpc_b200_code **out) {
+  if (!text) return fail(LDPC_B200_ERR_INVALID, "null text");
+  return wrap_code([&] { return new ldpc_code(std::string(text, len), false); }, out);
+}
+
+ldpc_b200_status ldpc_b200_code_from_csr(uint32_t n_checks, uint32_t n_vars, const uint32_t *row_ptr,
+                                         const uint32_t *col_idx, uint32_t n_erased_vars, ldpc_b200_code **out) {
+  if (!row_ptr || !col_idx || !n_checks || !n_vars) return fail(LDPC_B200_ERR_INVALID, "bad CSR arguments");
+  return wrap_code([&] { return new ldpc_code(n_checks, n_vars, row_ptr, col_idx, n_erased_vars); }, out);
+}
+
+void ldpc_b200_code_destroy(ldpc_b200_code *code) { delete code; }
+
+ldpc_b200_status ldpc_b200_code_get_info(const ldpc_b200_code *code, ldpc_b200_code_info *info) {
+  if (!code || !info) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  const ldpc_code &c = *code->code;
+  info->n_checks = uint32_t(c.n_outputs());
+  info->n_vars = uint32_t(c.n_inputs());
+  info->n_edges = c.n_edges();
+  info->n_erased_vars = uint32_t(c.n_erased_inputs());
+  info->n_erased_checks = uint32_t(c.n_erased_outputs());
+  info->max_deg_var = uint32_t(c.max_degree_in());
+  info->max_deg_check = uint32_t(c.max_degree_out());
+  info->row_ptr = c.row_ptr().data();
+  info->col_ptr = c.col_ptr().data();
+  info->in_to_out = c.in_to_out().data();
+  info->out_to_in = c.out_to_in().data();
+  info->out_edge_to_var = c.out_edge_to_var().data();
+  return LDPC_B200_OK;
+}
+
+void ldpc_b200_code_set_erased_vars(ldpc_b200_code *code, uint32_t n_erased) {
+  if (code) code->code->set_n_erased_in_bits(int32_t(n_erased));
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------ decoder object
+struct ldpc_b200_decoder {
+  int device = 0;
+  int precision = LDPC_B200_FP32;
+  uint32_t elem = 4; // sizeof(llr)
+  uint32_t M = 0, N = 0, E = 0, S = 0, W = 0, n_erased = 0;
+  uint32_t frames_in_flight = 1; // P exposed to callers (parallel_factor)
+  uint32_t P = 32, log2P = 5;    // allocated slots (>= 32)
+  uint32_t log2G = 3;            // 16-byte vectors per row
+  uint32_t log2PW = 0;           // 32-slot words per row
+  int n_sms = 1;
+  unsigned host_threads = 1;
+
+  dev_buf<uint32_t> d_row_ptr, d_col_ptr, d_in_to_out, d_edge_var;
+  dev_buf<uint8_t> d_msg, d_llr0, d_stage;
+  dev_buf<uint32_t> d_syn, d_hard, d_viol, d_stage_syn, d_retire_mask, d_new_mask, d_slot_entry, d_results;
+  dev_buf<dev::RefillEntry> d_refill;
+  dev_buf<dev::ExtractEntry> d_extract;
+  dev_buf<uint16_t> d_phi_table;
+  pinned_buf<uint8_t> h_stage;
+  pinned_buf<uint32_t> h_stage_syn, h_viol, h_results, h_mask, h_retire_mask, h_slot_entry;
+  pinned_buf<dev::RefillEntry> h_refill;
+  pinned_buf<dev::ExtractEntry> h_extract;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  int grid_cn = 1, grid_vn = 1, grid_vnb = 1, grid_misc = 1;
+  size_t smem_tab = 0;
+
+  ~ldpc_b200_decoder() {
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // ---- launches -----------------------------------------------------------
+  void launch_cn() {
+    if (precision == LDPC_B200_FP32)
+      dev::cn_update_kernel<dev::TraitsF32><<<grid_cn, dev::kThreads, 0, stream>>>(
+          reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), nullptr, M, log2G);
+    else
+      dev::cn_update_kernel<dev::TraitsF16><<<grid_cn, dev::kThreads, smem_tab, stream>>>(
+          reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p, M,
+          log2G);
+  }
+  void launch_vn(bool bits) {
+    uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p);
+    const uint4 *l0 = reinterpret_cast<const uint4 *>(d_llr0.p);
+    uint8_t *hard = reinterpret_cast<uint8_t *>(d_hard.p);
+    if (precision == LDPC_B200_FP32) {
+      if (bits)
+        dev::vn_update_kernel<dev::TraitsF32, true><<<grid_vnb, dev::kThreads, 0, stream>>>(
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G);
+      else
+        dev::vn_update_kernel<dev::TraitsF32, false><<<grid_vn, dev::kThreads, 0, stream>>>(
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G);
+    } else {
+      if (bits)
+        dev::vn_update_kernel<dev::TraitsF16, true><<<grid_vnb, dev::kThreads, smem_tab, stream>>>(
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G);
+      else
+        dev::vn_update_kernel<dev::TraitsF16, false><<<grid_vn, dev::kThreads, smem_tab, stream>>>(
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G);
+    }
+  }
+  void launch_check() {
+    cudaMemsetAsync(d_viol.p, 0, sizeof(uint32_t) << log2PW, stream);
+    dev::syndrome_check_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, d_hard.p, d_row_ptr.p, d_edge_var.p,
+                                                                        d_viol.p, M, log2PW);
+  }
+  // entries (h_refill[0..n)) -> device, then scatter priors, first messages and syndromes
+  void launch_refill(uint32_t n_new, const void *src, const uint32_t *src_syn, int channel, float param) {
+    // slot masks / entry index per slot
+    const uint32_t PW = 1u << log2PW;
+    std::fill(h_mask.p, h_mask.p + PW, 0u);
+    for (uint32_t t = 0; t < n_new; ++t) {
+      const uint32_t s = h_refill.p[t].slot;
+      h_mask.p[s >> 5] |= 1u << (s & 31);
+      h_slot_entry.p[s] = t;
+    }
+    cudaMemcpyAsync(d_refill.p, h_refill.p, sizeof(dev::RefillEntry) * n_new, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_new_mask.p, h_mask.p, sizeof(uint32_t) * PW, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_slot_entry.p, h_slot_entry.p, sizeof(uint32_t) * P, cudaMemcpyHostToDevice, stream);
+    const uint32_t n_regular = N - n_erased;
+    if (precision == LDPC_B200_FP32)
+      dev::refill_kernel<dev::TraitsF32, float><<<grid_misc, dev::kThreads, 0, stream>>>(
+          reinterpret_cast<float *>(d_msg.p), reinterpret_cast<float *>(d_llr0.p), static_cast<const float *>(src),
+          d_refill.p, n_new, d_col_ptr.p, d_in_to_out.p, nullptr, N, n_regular, log2P, channel, param);
+    else
+      dev::refill_kernel<dev::TraitsF16, uint16_t><<<grid_misc, dev::kThreads, 0, stream>>>(
+          reinterpret_cast<uint16_t *>(d_msg.p), reinterpret_cast<uint16_t *>(d_llr0.p),
+          static_cast<const uint16_t *>(src), d_refill.p, n_new, d_col_ptr.p, d_in_to_out.p, d_phi_table.p, N,
+          n_regular, log2P, channel, param);
+    dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_new_mask.p,
+                                                                         d_slot_entry.p, M, log2PW);
+  }
+  // h_extract[slot].dst_offset valid for every slot set in h_retire_mask
+  void launch_extract(uint32_t *dst) {
+    const uint32_t PW = 1u << log2PW;
+    cudaMemcpyAsync(d_retire_mask.p, h_retire_mask.p, sizeof(uint32_t) * PW, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_extract.p, h_extract.p, sizeof(dev::ExtractEntry) * P, cudaMemcpyHostToDevice, stream);
+    dev::extract_kernel<<<grid_misc, 128, 0, stream>>>(d_hard.p, dst, d_retire_mask.p, d_extract.p, W, log2PW);
+  }
+};
+
+namespace {
+
+template <typename K> int occupancy_grid(K kernel, int threads, size_t smem, int n_sms, uint64_t items) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const uint64_t need = (items + threads - 1) / threads;
+  return int(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(per_sm) * n_sms, need)));
+}
+
+} // namespace
+
+extern "C" {
+
+ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ldpc_b200_config *cfg,
+                                          ldpc_b200_decoder **out) {
+  if (!code_h || !cfg || !out) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const ldpc_code &code = *code_h->code;
+  if (code.n_inputs() & 0x1F) // ldpc_decoder_gpu.cu:30-32
+    return fail(LDPC_B200_ERR_MULTIPLE_32, "This decoder only handles input sizes that are multiple of 32");
+  if (!code.structure_ok()) return fail(LDPC_B200_ERR_CODE, "Incorrect code structure\n"); // :40-58
+  if (cfg->precision != LDPC_B200_FP32 && cfg->precision != LDPC_B200_FP16)
+    return fail(LDPC_B200_ERR_INVALID, "unknown precision");
+
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(LDPC_B200_ERR_CUDA, "no CUDA device: the B200 decoder has no CPU fallback");
+  }
+  std::unique_ptr<ldpc_b200_decoder> d(new ldpc_b200_decoder);
+  if (cfg->device >= 0) {
+    CU_TRY(cudaSetDevice(cfg->device));
+    d->device = cfg->device;
+  } else {
+    CU_TRY(cudaGetDevice(&d->device));
+  }
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, d->device));
+  d->n_sms = prop.multiProcessorCount;
+  d->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  d->precision = cfg->precision;
+  d->elem = cfg->precision == LDPC_B200_FP32 ? 4 : 2;
+  d->M = uint32_t(code.n_outputs());
+  d->N = uint32_t(code.n_inputs());
+  d->E = code.n_edges();
+  d->S = (d->M + 31) >> 5;
+  d->W = d->N >> 5;
+  d->n_erased = uint32_t(code.n_erased_inputs());
+  if (d->n_erased > d->N) return fail(LDPC_B200_ERR_INVALID, "more punctured variables than variables");
+
+  // frames in flight from device memory (ldpc_decoder_gpu.cu:67-99), with this layout's own per-frame cost:
+  // messages + priors + staging + bit-sliced syndromes/decisions + packed results
+  size_t free_b = 0, total_b = 0;
+  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t graph_bytes = 4ull * (uint64_t(d->M) + d->N + 2ull * d->E + 2);
+  const uint64_t per_frame = uint64_t(d->elem) * (uint64_t(d->E) + 2ull * d->N) + 2ull * (d->M >> 3) + 8ull * d->S +
+                             (d->N >> 3) * 2ull + 64;
+  const uint32_t headroom = cfg->mem_headroom_pct ? cfg->mem_headroom_pct : 10;
+  const uint64_t usable = uint64_t(double(free_b) * (100.0 - std::min(headroom, 90u)) / 100.0);
+  if (usable < graph_bytes + per_frame * 32) return fail(LDPC_B200_ERR_NOMEM, "code does not fit in device memory");
+  const uint64_t fit = (usable - graph_bytes) / per_frame;
+  uint32_t log2_frames = std::min<uint32_t>(ilog2(fit), std::min<uint32_t>(cfg->max_log2_frames, 13u));
+  d->frames_in_flight = 1u << log2_frames;
+  d->log2P = std::max<uint32_t>(log2_frames, 5u);
+  d->P = 1u << d->log2P;
+  d->log2G = d->log2P - (d->precision == LDPC_B200_FP32 ? 2 : 3);
+  d->log2PW = d->log2P - 5;
+
+  const size_t P = d->P;
+  CU_TRY(d->d_row_ptr.alloc(d->M + 1));
+  CU_TRY(d->d_col_ptr.alloc(d->N + 1));
+  CU_TRY(d->d_in_to_out.alloc(d->E));
+  CU_TRY(d->d_edge_var.alloc(d->E));
+  CU_TRY(cudaMemcpy(d->d_row_ptr.p, code.row_ptr().data(), 4ull * (d->M + 1), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d->d_col_ptr.p, code.col_ptr().data(), 4ull * (d->N + 1), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d->d_in_to_out.p, code.in_to_out().data(), 4ull * d->E, cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d->d_edge_var.p, code.out_edge_to_var().data(), 4ull * d->E, cudaMemcpyHostToDevice));
+  CU_TRY(d->d_msg.alloc(size_t(d->E) * P * d->elem));
+  CU_TRY(d->d_llr0.alloc(size_t(d->N) * P * d->elem));
+  CU_TRY(d->d_stage.alloc(size_t(d->N) * P * d->elem));
+  CU_TRY(d->d_syn.alloc(size_t(d->M) << d->log2PW));
+  CU_TRY(d->d_hard.alloc(size_t(d->N) << d->log2PW));
+  CU_TRY(d->d_viol.alloc(P / 32));
+  CU_TRY(d->d_stage_syn.alloc(size_t(d->S) * P));
+  CU_TRY(d->d_retire_mask.alloc(P / 32));
+  CU_TRY(d->d_new_mask.alloc(P / 32));
+  CU_TRY(d->d_slot_entry.alloc(P));
+  CU_TRY(d->d_results.alloc(size_t(d->W) * P));
+  CU_TRY(d->d_refill.alloc(P));
+  CU_TRY(d->d_extract.alloc(P));
+  CU_TRY(d->d_phi_table.alloc(dev::kPhiTableSize));
+  CU_TRY(cudaMemset(d->d_msg.p, 0, size_t(d->E) * P * d->elem));
+  CU_TRY(cudaMemset(d->d_llr0.p, 0, size_t(d->N) * P * d->elem));
+  CU_TRY(cudaMemset(d->d_syn.p, 0, (size_t(d->M) << d->log2PW) * 4));
+  CU_TRY(cudaMemset(d->d_hard.p, 0, (size_t(d->N) << d->log2PW) * 4));
+  CU_TRY(d->h_stage.alloc(size_t(d->N) * P * d->elem));
+  CU_TRY(d->h_stage_syn.alloc(size_t(d->S) * P));
+  CU_TRY(d->h_viol.alloc(P / 32));
+  CU_TRY(d->h_results.alloc(size_t(d->W) * P));
+  CU_TRY(d->h_mask.alloc(P / 32));
+  CU_TRY(d->h_retire_mask.alloc(P / 32));
+  CU_TRY(d->h_slot_entry.alloc(P));
+  CU_TRY(d->h_refill.alloc(P));
+  CU_TRY(d->h_extract.alloc(P));
+  CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreate(&d->ev_a));
+  CU_TRY(cudaEventCreate(&d->ev_b));
+
+  dev::build_phi_table_kernel<<<dev::kPhiTableSize / 256, 256, 0, d->stream>>>(d->d_phi_table.p);
+  CU_TRY(cudaGetLastError());
+
+  // persistent grids: SMs x resident CTAs
+  d->smem_tab = d->precision == LDPC_B200_FP16 ? size_t(dev::kPhiTableSize) * 2 : 0;
+  const uint64_t cn_items = uint64_t(d->M) << d->log2G, vn_items = uint64_t(d->N) << d->log2G;
+  if (d->precision == LDPC_B200_FP32) {
+    d->grid_cn = occupancy_grid(dev::cn_update_kernel<dev::TraitsF32>, dev::kThreads, 0, d->n_sms, cn_items);
+    d->grid_vn = occupancy_grid(dev::vn_update_kernel<dev::TraitsF32, false>, dev::kThreads, 0, d->n_sms, vn_items);
+    d->grid_vnb = occupancy_grid(dev::vn_update_kernel<dev::TraitsF32, true>, dev::kThreads, 0, d->n_sms, vn_items);
+  } else {
+    CU_TRY(cudaFuncSetAttribute(dev::cn_update_kernel<dev::TraitsF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(d->smem_tab)));
+    CU_TRY(cudaFuncSetAttribute(dev::vn_update_kernel<dev::TraitsF16, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
+    CU_TRY(cudaFuncSetAttribute(dev::vn_update_kernel<dev::TraitsF16, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
+    d->grid_cn = occupancy_grid(dev::cn_update_kernel<dev::TraitsF16>, dev::kThreads, d->smem_tab, d->n_sms, cn_items);
+    d->grid_vn = occupancy_grid(dev::vn_update_kernel<dev::TraitsF16, false>, dev::kThreads, d->smem_tab, d->n_sms,
+                                vn_items);
+    d->grid_vnb = occupancy_grid(dev::vn_update_kernel<dev::TraitsF16, true>, dev::kThreads, d->smem_tab, d->n_sms,
+                                 vn_items);
+  }
+  d->grid_misc = d->n_sms * 8;
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  *out = d.release();
+  return LDPC_B200_OK;
+}
+
+void ldpc_b200_decoder_destroy(ldpc_b200_decoder *dec) {
+  if (!dec) return;
+  cudaSetDevice(dec->device);
+  delete dec;
+}
+
+uint32_t ldpc_b200_decoder_frames_in_flight(const ldpc_b200_decoder *dec) { return dec ? dec->frames_in_flight : 0; }
+
+void ldpc_b200_decoder_set_erased_vars(ldpc_b200_decoder *dec, uint32_t n_erased) {
+  if (dec && n_erased <= dec->N) dec->n_erased = n_erased;
+}
+
+uint64_t ldpc_b200_bytes_per_frame_iteration(const ldpc_b200_decoder *dec) {
+  if (!dec) return 0;
+  return (4ull * dec->E + dec->N) * dec->elem + 4ull * dec->S;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------ staging of new frames
+namespace {
+
+struct input_view {
+  const uint8_t *base;     // host or device
+  const uint32_t *syn;     // host or device
+  bool on_device, syn_on_device;
+  int layout;
+  uint64_t frame_stride;   // FRAME_MAJOR
+  uint32_t n_cols;         // frames physically present (pool or n_frames)
+};
+
+// Fill h_refill[t] for new frames [first, first+cnt) going to slots[t]; stage host data if needed.
+// Returns device pointers the refill kernels should read.
+ldpc_b200_status stage_frames(ldpc_b200_decoder *d, const input_view &in, uint32_t first, uint32_t cnt,
+                              const uint32_t *slots, const void **src_dev, const uint32_t **syn_dev,
+                              ldpc_b200_report *rep) {
+  const uint32_t n_reg = d->N - d->n_erased;
+  const size_t es = d->elem;
+  for (uint32_t t = 0; t < cnt; ++t) {
+    const uint32_t col = (first + t) % in.n_cols;
+    dev::RefillEntry &en = d->h_refill.p[t];
+    en.slot = slots[t];
+    en.pad = 0;
+    if (in.on_device) {
+      if (in.layout == LDPC_B200_LAYOUT_INTERLEAVED) {
+        en.src_offset = col;
+        en.src_stride = in.n_cols;
+      } else {
+        en.src_offset = uint64_t(col) * in.frame_stride;
+        en.src_stride = 1;
+      }
+    } else { // staged as [n_reg][cnt] (interleaved) or [cnt][n_reg] (frame-major)
+      if (in.layout == LDPC_B200_LAYOUT_INTERLEAVED) {
+        en.src_offset = t;
+        en.src_stride = cnt;
+      } else {
+        en.src_offset = uint64_t(t) * n_reg;
+        en.src_stride = 1;
+      }
+    }
+    en.syn_offset = in.syn_on_device ? uint64_t(col) * d->S : uint64_t(t) * d->S;
+  }
+  if (in.on_device) {
+    *src_dev = in.base;
+  } else {
+    uint8_t *stage = d->h_stage.p;
+    if (in.layout == LDPC_B200_LAYOUT_INTERLEAVED) {
+      // prepare_vectors (ldpc_decoder_gpu.cu:199-207): rows of cnt consecutive frames, split where the pool wraps
+      const uint32_t c0 = first % in.n_cols;
+      parallel_for(n_reg, d->host_threads, [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+          uint8_t *dst = stage + i * cnt * es;
+          const uint8_t *row = in.base + i * size_t(in.n_cols) * es;
+          uint32_t done = 0, col = c0;
+          while (done < cnt) {
+            const uint32_t run = std::min(cnt - done, in.n_cols - col);
+            memcpy(dst + size_t(done) * es, row + size_t(col) * es, size_t(run) * es);
+            done += run;
+            col = 0;
+          }
+        }
+      });
+    } else {
+      parallel_for(cnt, d->host_threads, [&](size_t a, size_t b) {
+        for (size_t t = a; t < b; ++t) {
+          const uint32_t col = uint32_t((first + t) % in.n_cols);
+          memcpy(stage + t * size_t(n_reg) * es, in.base + size_t(col) * in.frame_stride * es, size_t(n_reg) * es);
+        }
+      });
+    }
+    const size_t bytes = size_t(n_reg) * cnt * es;
+    CU_TRY(cudaMemcpyAsync(d->d_stage.p, stage, bytes, cudaMemcpyHostToDevice, d->stream));
+    if (rep) rep->h2d_bytes += bytes;
+    *src_dev = d->d_stage.p;
+  }
+  if (in.syn_on_device) {
+    *syn_dev = in.syn;
+  } else {
+    for (uint32_t t = 0; t < cnt; ++t) {
+      const uint32_t col = (first + t) % in.n_cols;
+      memcpy(d->h_stage_syn.p + size_t(t) * d->S, in.syn + size_t(col) * d->S, size_t(d->S) * 4);
+    }
+    CU_TRY(cudaMemcpyAsync(d->d_stage_syn.p, d->h_stage_syn.p, size_t(d->S) * cnt * 4, cudaMemcpyHostToDevice,
+                           d->stream));
+    if (rep) rep->h2d_bytes += size_t(d->S) * cnt * 4;
+    *syn_dev = d->d_stage_syn.p;
+  }
+  return LDPC_B200_OK;
+}
+
+// Retire the frames sitting in slots[0..cnt) -> results rows frames[0..cnt)
+ldpc_b200_status retire_frames(ldpc_b200_decoder *d, uint32_t cnt, const uint32_t *slots, const uint32_t *frames,
+                               uint32_t *results, bool results_on_device, ldpc_b200_report *rep) {
+  const uint32_t PW = 1u << d->log2PW;
+  std::fill(d->h_retire_mask.p, d->h_retire_mask.p + PW, 0u);
+  for (uint32_t t = 0; t < cnt; ++t) {
+    const uint32_t s = slots[t];
+    d->h_retire_mask.p[s >> 5] |= 1u << (s & 31);
+    d->h_extract.p[s].dst_offset = results_on_device ? uint64_t(frames[t]) * d->W : uint64_t(t) * d->W;
+  }
+  d->launch_extract(results_on_device ? results : d->d_results.p);
+  CU_TRY(cudaGetLastError());
+  if (!results_on_device) {
+    const size_t bytes = size_t(d->W) * cnt * 4;
+    CU_TRY(cudaMemcpyAsync(d->h_results.p, d->d_results.p, bytes, cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaStreamSynchronize(d->stream));
+    for (uint32_t t = 0; t < cnt; ++t)
+      memcpy(results + size_t(frames[t]) * d->W, d->h_results.p + size_t(t) * d->W, size_t(d->W) * 4);
+    if (rep) rep->d2h_bytes += bytes;
+  }
+  return LDPC_B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm, uint32_t n_frames,
+                                  const void *input, const uint32_t *syndromes, uint32_t *results,
+                                  ldpc_b200_report *report, uint32_t *iter_counts) {
+  if (!d || !prm) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  if (n_frames == 0) return LDPC_B200_OK; // ldpc_decoder_gpu.cu:293-294
+  if (!input || !syndromes || !results) return fail(LDPC_B200_ERR_INVALID, "null buffer");
+  if (prm->num_iter_check_parity == 0) return fail(LDPC_B200_ERR_INVALID, "num_iter_check_parity must be > 0");
+  CU_TRY(cudaSetDevice(d->device));
+  const double t0 = now_s();
+  ldpc_b200_report rep;
+  memset(&rep, 0, sizeof(rep));
+
+  input_view in;
+  in.base = static_cast<const uint8_t *>(input);
+  in.syn = syndromes;
+  in.on_device = is_device_pointer(input);
+  in.syn_on_device = is_device_pointer(syndromes);
+  in.layout = prm->input_layout;
+  in.frame_stride = prm->frame_stride ? prm->frame_stride : (d->N - d->n_erased);
+  in.n_cols = prm->input_pool_frames ? prm->input_pool_frames : n_frames;
+  const bool results_on_device = is_device_pointer(results);
+  const bool simd_pairs = (prm->flags & LDPC_B200_FLAG_SIMD_PAIRS) != 0;
+  const uint32_t B = std::min(n_frames, d->frames_in_flight); // num_vectors_gpu_batch
+  const uint32_t k_check = prm->num_iter_check_parity;
+
+  // position j of the reference's slot order -> (frame id, physical slot).  The reference physically
+  // permutes frames (flood_permute_vecs); here only this table is permuted.
+  std::vector<uint32_t> in_gpu(B), virt(B);
+  std::vector<uint32_t> iter_start(n_frames, uint32_t(-1)), iter_end(n_frames, uint32_t(-1));
+  std::vector<uint8_t> stop(B);
+  std::vector<uint32_t> origin, dest, tmp_slots(B), tmp_frames(B);
+  for (uint32_t j = 0; j < B; ++j) in_gpu[j] = virt[j] = j;
+
+  cudaEvent_t ev_first, ev_last;
+  CU_TRY(cudaEventCreate(&ev_first));
+  CU_TRY(cudaEventCreate(&ev_last));
+  struct ev_guard {
+    cudaEvent_t a, b;
+    ~ev_guard() {
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+    }
+  } guard{ev_first, ev_last};
+
+  const void *src_dev = nullptr;
+  const uint32_t *syn_dev = nullptr;
+  ldpc_b200_status st = stage_frames(d, in, 0, B, virt.data(), &src_dev, &syn_dev, &rep);
+  if (st != LDPC_B200_OK) return st;
+  CU_TRY(cudaEventRecord(ev_first, d->stream));
+  d->launch_refill(B, src_dev, syn_dev, prm->channel, prm->channel_param);
+  rep.other_launches += 2;
+  CU_TRY(cudaGetLastError());
+
+  uint32_t next_to_load = B, g = 0;
+  double t_iter0 = now_s(), t_iter1 = t_iter0;
+  for (;;) {
+    d->launch_cn();
+    rep.cn_launches++;
+    const bool check = g > 0 && (g % k_check) == 0; // :350
+    if (!check) {
+      d->launch_vn(false);
+      rep.vn_launches++;
+    } else {
+      d->launch_vn(true);
+      rep.vn_launches++;
+      d->launch_check();
+      rep.other_launches++;
+      rep.n_checks_run++;
+      CU_TRY(cudaMemcpyAsync(d->h_viol.p, d->d_viol.p, sizeof(uint32_t) << d->log2PW, cudaMemcpyDeviceToHost,
+                             d->stream));
+      CU_TRY(cudaStreamSynchronize(d->stream));
+      rep.d2h_bytes += sizeof(uint32_t) << d->log2PW;
+      uint32_t n_stop = 0;
+      for (uint32_t j = 0; j < B; ++j) { // stop rule, :395-403
+        const uint32_t s = virt[j];
+        const bool violated = (d->h_viol.p[s >> 5] >> (s & 31)) & 1u;
+        const uint32_t n_it = g - iter_start[in_gpu[j]];
+        stop[j] = (!violated || n_it >= prm->num_iter_max) ? 1 : 0;
+        if (stop[j]) {
+          ++n_stop;
+          if (iter_end[in_gpu[j]] == uint32_t(-1)) iter_end[in_gpu[j]] = g;
+        }
+      }
+      if (next_to_load == n_frames && n_stop == B) { // everything loaded and finished, :414-462
+        t_iter1 = now_s();
+        st = retire_frames(d, B, virt.data(), in_gpu.data(), results, results_on_device, &rep);
+        if (st != LDPC_B200_OK) return st;
+        rep.other_launches++;
+        break;
+      }
+      uint32_t n_new = std::min(n_frames - next_to_load, n_stop); // :464
+      if (simd_pairs) n_new &= ~1u;                               // ldpc_decoder_gpu.cpp:623
+      if (n_new > 0) {
+        // bring n_new finished frames to positions [0,n_new) of the slot order (:487-516)
+        uint32_t ctr = 0;
+        for (uint32_t i = 0; i < n_new; ++i) ctr += stop[i];
+        const uint32_t n_swaps = n_new - ctr;
+        uint32_t o = 0, q = n_new;
+        for (uint32_t i = 0; i < n_swaps; ++i) {
+          while (stop[o]) ++o;
+          while (!stop[q]) ++q;
+          std::swap(in_gpu[o], in_gpu[q]);
+          std::swap(virt[o], virt[q]);
+          ++o;
+          ++q;
+        }
+        for (uint32_t j = 0; j < n_new; ++j) {
+          tmp_slots[j] = virt[j];
+          tmp_frames[j] = in_gpu[j];
+        }
+        st = retire_frames(d, n_new, tmp_slots.data(), tmp_frames.data(), results, results_on_device, &rep);
+        if (st != LDPC_B200_OK) return st;
+        st = stage_frames(d, in, next_to_load, n_new, tmp_slots.data(), &src_dev, &syn_dev, &rep);
+        if (st != LDPC_B200_OK) return st;
+        d->launch_refill(n_new, src_dev, syn_dev, prm->channel, prm->channel_param);
+        rep.other_launches += 3;
+        for (uint32_t j = 0; j < n_new; ++j) { // :604-609
+          in_gpu[j] = next_to_load + j;
+          iter_start[next_to_load + j] = g;
+        }
+        next_to_load += n_new;
+      }
+    }
+    CU_TRY(cudaGetLastError());
+    ++g;
+  }
+  CU_TRY(cudaEventRecord(ev_last, d->stream));
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, ev_first, ev_last));
+  rep.device_s = ms * 1e-3;
+
+  rep.max_iter = 0; // :616-628
+  rep.min_iter = uint32_t(-1);
+  double avg = 0;
+  for (uint32_t j = 0; j < n_frames; ++j) {
+    const uint32_t n = iter_end[j] - iter_start[j];
+    rep.max_iter = std::max(rep.max_iter, n);
+    rep.min_iter = std::min(rep.min_iter, n);
+    avg += n;
+    if (iter_counts) iter_counts[j] = n;
+  }
+  rep.avg_iter = float(avg / n_frames);
+  rep.iter_time_per_vector = float((t_iter1 - t_iter0) / (double(g) * B));
+  rep.global_iters = g;
+  rep.elapsed_s = now_s() - t0;
+  if (report) *report = rep;
+  return LDPC_B200_OK;
+}
+
+// ------------------------------------------------------------------ kernel-level entry points
+ldpc_b200_status ldpc_b200_debug_refill(ldpc_b200_decoder *d, int32_t channel, float channel_param, uint32_t cnt,
+                                        const void *staged, const uint32_t *syndromes) {
+  if (!d || !staged || !syndromes || cnt == 0 || cnt > d->P) return fail(LDPC_B200_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(d->device));
+  input_view in;
+  in.base = static_cast<const uint8_t *>(staged);
+  in.syn = syndromes;
+  in.on_device = is_device_pointer(staged);
+  in.syn_on_device = is_device_pointer(syndromes);
+  in.layout = LDPC_B200_LAYOUT_INTERLEAVED;
+  in.frame_stride = 0;
+  in.n_cols = cnt;
+  std::vector<uint32_t> slots(cnt);
+  for (uint32_t j = 0; j < cnt; ++j) slots[j] = j;
+  const void *src_dev = nullptr;
+  const uint32_t *syn_dev = nullptr;
+  ldpc_b200_status st = stage_frames(d, in, 0, cnt, slots.data(), &src_dev, &syn_dev, nullptr);
+  if (st != LDPC_B200_OK) return st;
+  d->launch_refill(cnt, src_dev, syn_dev, channel, channel_param);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_debug_iterate(ldpc_b200_decoder *d, uint32_t n_iters, int32_t final_bits, float *cn_ms,
+                                         float *vn_ms) {
+  if (!d) return fail(LDPC_B200_ERR_INVALID, "null decoder");
+  CU_TRY(cudaSetDevice(d->device));
+  float cn_acc = 0, vn_acc = 0;
+  const bool timed = cn_ms || vn_ms;
+  cudaEvent_t e0 = d->ev_a, e1 = d->ev_b, e2 = nullptr;
+  if (timed) CU_TRY(cudaEventCreate(&e2));
+  for (uint32_t it = 0; it < n_iters; ++it) {
+    if (timed) CU_TRY(cudaEventRecord(e0, d->stream));
+    d->launch_cn();
+    if (timed) CU_TRY(cudaEventRecord(e1, d->stream));
+    d->launch_vn(final_bits && it + 1 == n_iters);
+    if (timed) {
+      CU_TRY(cudaEventRecord(e2, d->stream));
+      CU_TRY(cudaEventSynchronize(e2));
+      float a = 0, b = 0;
+      CU_TRY(cudaEventElapsedTime(&a, e0, e1));
+      CU_TRY(cudaEventElapsedTime(&b, e1, e2));
+      cn_acc += a;
+      vn_acc += b;
+    }
+  }
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  if (e2) cudaEventDestroy(e2);
+  if (cn_ms) *cn_ms = cn_acc;
+  if (vn_ms) *vn_ms = vn_acc;
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_debug_cn_pass(ldpc_b200_decoder *d) {
+  if (!d) return fail(LDPC_B200_ERR_INVALID, "null decoder");
+  CU_TRY(cudaSetDevice(d->device));
+  d->launch_cn();
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_debug_vn_pass(ldpc_b200_decoder *d, int32_t final_bits) {
+  if (!d) return fail(LDPC_B200_ERR_INVALID, "null decoder");
+  CU_TRY(cudaSetDevice(d->device));
+  d->launch_vn(final_bits != 0);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_debug_check(ldpc_b200_decoder *d, uint8_t *violated) {
+  if (!d || !violated) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(d->device));
+  d->launch_check();
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(d->h_viol.p, d->d_viol.p, sizeof(uint32_t) << d->log2PW, cudaMemcpyDeviceToHost, d->stream));
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  for (uint32_t s = 0; s < d->P; ++s) violated[s] = (d->h_viol.p[s >> 5] >> (s & 31)) & 1u;
+  return LDPC_B200_OK;
+}
+
+static ldpc_b200_status read_column(ldpc_b200_decoder *d, const uint8_t *src, uint64_t rows, uint32_t slot, float *out) {
+  if (slot >= d->P) return fail(LDPC_B200_ERR_INVALID, "slot out of range");
+  CU_TRY(cudaSetDevice(d->device));
+  dev_buf<uint8_t> tmp;
+  CU_TRY(tmp.alloc(rows * d->elem));
+  const unsigned blocks = unsigned((rows + 255) / 256);
+  std::vector<uint8_t> host(rows * d->elem);
+  if (d->elem == 4)
+    dev::gather_slot_kernel<float><<<blocks, 256, 0, d->stream>>>(reinterpret_cast<const float *>(src),
+                                                                  reinterpret_cast<float *>(tmp.p), rows, d->log2P, slot);
+  else
+    dev::gather_slot_kernel<uint16_t><<<blocks, 256, 0, d->stream>>>(
+        reinterpret_cast<const uint16_t *>(src), reinterpret_cast<uint16_t *>(tmp.p), rows, d->log2P, slot);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(host.data(), tmp.p, rows * d->elem, cudaMemcpyDeviceToHost, d->stream));
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  if (d->elem == 4) {
+    memcpy(out, host.data(), rows * 4);
+  } else {
+    const __half *h = reinterpret_cast<const __half *>(host.data());
+    for (uint64_t i = 0; i < rows; ++i) out[i] = __half2float(h[i]);
+  }
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_debug_read_messages(ldpc_b200_decoder *d, uint32_t slot, float *out_e) {
+  if (!d || !out_e) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  return read_column(d, d->d_msg.p, d->E, slot, out_e);
+}
+
+ldpc_b200_status ldpc_b200_debug_read_priors(ldpc_b200_decoder *d, uint32_t slot, float *out_n) {
+  if (!d || !out_n) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  return read_column(d, d->d_llr0.p, d->N, slot, out_n);
+}
+
+ldpc_b200_status ldpc_b200_debug_read_hard(ldpc_b200_decoder *d, uint32_t slot, uint32_t *out_words) {
+  if (!d || !out_words || slot >= d->P) return fail(LDPC_B200_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(d->device));
+  uint32_t frame0 = 0;
+  ldpc_b200_status st = retire_frames(d, 1, &slot, &frame0, out_words, false, nullptr);
+  return st;
+}
+
+ldpc_b200_status ldpc_b200_phi_table_fp16(ldpc_b200_decoder *d, uint16_t *table) {
+  if (!d || !table) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(d->device));
+  CU_TRY(cudaMemcpy(table, d->d_phi_table.p, dev::kPhiTableSize * 2, cudaMemcpyDeviceToHost));
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_debug_phi_abs_f32(const float *x, float *y, size_t n) {
+  if (!x || !y) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  dev_buf<float> dx, dy;
+  CU_TRY(dx.alloc(n));
+  CU_TRY(dy.alloc(n));
+  CU_TRY(cudaMemcpy(dx.p, x, n * 4, cudaMemcpyHostToDevice));
+  dev::phi_abs_f32_kernel<<<unsigned((n + 255) / 256), 256>>>(dx.p, dy.p, n);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpy(y, dy.p, n * 4, cudaMemcpyDeviceToHost));
+  return LDPC_B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,490 @@
+// ldpc_kernels.cuh -- sm_100a device kernels of the B200 flood decoder.
+//
+// Data layout in HBM (P = frame slots, power of two >= 32; s = sizeof(llr)):
+//   msg   [E][P]      llr   check-major edge id, frame slot fastest (one array, updated in place:
+//                           v2c in the "phi domain" after a variable-node pass, c2v after a check-node pass)
+//   llr0  [N][P]      llr   channel priors
+//   syn   [M][P/32]   u32   target syndromes, bit-sliced over slots (slot s <-> byte s>>3, bit s&7)
+//   hard  [N][P/32]   u32   posterior hard decisions, bit-sliced the same way
+//   viol  [P/32]      u32   "some check violated" bit per slot
+// A thread owns one 16-byte vector of a row: 4 frames in fp32, 8 frames in fp16 (4 half2 words).
+// All per-word arithmetic goes through a Traits struct so both precisions share the kernels.
+//
+// What each kernel replaces in the reference (src/cuda/flood.cu):
+//   cn_update_kernel      flood_backward              :77-115
+//   vn_update_kernel      flood_forward[_w_final_bits] :117-189
+//   syndrome_check_kernel check_parity                :191-223 (on bit-sliced words, 32 frames per XOR)
+//   refill_kernel         llr_bsc/llr_biawgn + flood_refill :47-75, 297-329 (direct to freed slots)
+//   refill_syndrome_kernel flood_refill syndrome part :324-328
+//   extract_kernel        deinterlace_output          :277-295 (only retiring slots)
+// flood_permute_vecs (:225-275) has no equivalent: slots are indirect, frames never move.
+#pragma once
+
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace ldpc_b200 {
+namespace dev {
+
+constexpr int kMaxRegDeg = 8;       // rows of this degree or less are held in registers (one read, one write)
+constexpr int kThreads = 256;       // CTA size of the streaming kernels
+constexpr int kPhiTableSize = 32768; // fp16 phi_abs table entries (all non-negative half bit patterns)
+
+// ---------------------------------------------------------------- memory helpers
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) { // read once: evict-first
+  uint4 r;
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cached(const uint4 *p) { // re-read soon (large-degree rows): keep in L1/L2
+  uint4 r;
+  asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------- phi, fp32
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// phi_abs(x) = -ln tanh(x/2) on x >= 0, with the reference's clamp and Taylor switch
+// (flood.cu:14, 31-37): xm = max(x,1e-5); xm > 5 ? 2 e^-xm : ln((1+e^-xm)/(1-e^-xm)).
+// 3 MUFU (ex2, 2x lg2) instead of libm exp/expm1/log + IEEE divide.  The cancellation in
+// 1-e^-x for small x (expm1 in the reference) is avoided with a degree-6 series below 1/8.
+__device__ __forceinline__ float phi_abs_f32(float x) {
+  const float xm = fmaxf(x, 1.0e-5f);
+  const float e = ex2_approx(xm * -1.4426950408889634f);
+  // 1 - e^-x = x(1 - x/2 + x^2/6 - x^3/24 + x^4/120 - x^5/720), |rel err| < 1e-9 for x < 1/8
+  float q = fmaf(xm, -1.0f / 720.0f, 1.0f / 120.0f);
+  q = fmaf(xm, q, -1.0f / 24.0f);
+  q = fmaf(xm, q, 1.0f / 6.0f);
+  q = fmaf(xm, q, -0.5f);
+  q = fmaf(xm, q, 1.0f);
+  const float den = xm < 0.125f ? xm * q : 1.0f - e;
+  const float num = 2.0f - den; // 1 + e^-x
+  const float r = 0.6931471805599453f * (lg2_approx(num) - lg2_approx(den));
+  return xm > 5.0f ? e + e : r;
+}
+
+// ---------------------------------------------------------------- per-word traits
+// A "word" is 32 bits of a message vector: one float, or two halves.
+struct TraitsF32 {
+  static constexpr int kFramesPerWord = 1;
+  static constexpr int kFramesPerVec = 4;
+  static constexpr uint32_t kSignMask = 0x80000000u;
+  static constexpr bool kUsesTable = false;
+  __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFFFFFFu; }
+  __device__ static __forceinline__ uint32_t add_w(uint32_t a, uint32_t b) {
+    return __float_as_uint(__uint_as_float(a) + __uint_as_float(b));
+  }
+  __device__ static __forceinline__ uint32_t sub_w(uint32_t a, uint32_t b) {
+    return __float_as_uint(__uint_as_float(a) - __uint_as_float(b));
+  }
+  // phi_abs of a word that may be negative (clamped like the reference's fmax)
+  __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *) {
+    return __float_as_uint(phi_abs_f32(__uint_as_float(w)));
+  }
+  // sign word with bit set where the frame's bit is 1 (bits = low kFramesPerWord bits)
+  __device__ static __forceinline__ uint32_t sign_from_bits(uint32_t bits) { return bits << 31; }
+  // hard decision bits of a posterior word: bit=1 <=> sign bit clear (flood.cu:180)
+  __device__ static __forceinline__ uint32_t hard_bits(uint32_t w) { return (~w) >> 31; }
+  // channel value -> llr (flood.cu:58, :73)
+  __device__ static __forceinline__ uint32_t to_llr(uint32_t raw, int channel, float param) {
+    const float x = __uint_as_float(raw);
+    if (channel == 1) return (__float_as_uint(param) & 0x7FFFFFFFu) | (raw & 0x80000000u);
+    if (channel == 0) return __float_as_uint(x * param);
+    return raw;
+  }
+};
+
+struct TraitsF16 {
+  static constexpr int kFramesPerWord = 2;
+  static constexpr int kFramesPerVec = 8;
+  static constexpr uint32_t kSignMask = 0x80008000u;
+  static constexpr bool kUsesTable = true;
+  __device__ static __forceinline__ __half2 h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
+  __device__ static __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+  __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFF7FFFu; }
+  // one IEEE half rounding per add/sub, as the reference's scalar __half arithmetic (flood.cu:95-99, 134-147)
+  __device__ static __forceinline__ uint32_t add_w(uint32_t a, uint32_t b) { return u32(__hadd2_rn(h2(a), h2(b))); }
+  __device__ static __forceinline__ uint32_t sub_w(uint32_t a, uint32_t b) { return u32(__hsub2_rn(h2(a), h2(b))); }
+  __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *tab) {
+    // negative / NaN preimages clamp to the table's first entry (flood.cu:10, 26)
+    const uint32_t c = u32(__hmax2(h2(w), h2(0u)));
+    const uint32_t lo = tab[c & 0x7FFFu];
+    const uint32_t hi = tab[(c >> 16) & 0x7FFFu];
+    return lo | (hi << 16);
+  }
+  __device__ static __forceinline__ uint32_t sign_from_bits(uint32_t bits) {
+    return ((bits & 1u) << 15) | ((bits & 2u) << 30);
+  }
+  __device__ static __forceinline__ uint32_t hard_bits(uint32_t w) {
+    const uint32_t n = ~w;
+    return ((n >> 15) & 1u) | ((n >> 30) & 2u);
+  }
+  __device__ static __forceinline__ uint16_t to_llr(uint16_t raw, int channel, float param) {
+    const __half ph = __float2half_rn(param); // float -> llr_t kernel argument
+    const uint16_t pb = __half_as_ushort(ph);
+    if (channel == 1) return (pb & 0x7FFFu) | (raw & 0x8000u);
+    if (channel == 0) return __half_as_ushort(__hmul(__ushort_as_half(raw), ph));
+    return raw;
+  }
+};
+
+// reference fp16 phi_abs (flood.cu:21-29), used once to fill the table
+__device__ __forceinline__ __half phi_abs_f16_exact(__half x) {
+  const __half limit = __ushort_as_half(0x4500); // 5
+  const __half pre = __ushort_as_half(0x003f);
+  const __half two = __ushort_as_half(0x4000);
+  const __half half_one = __ushort_as_half(0x3800);
+  const __half xm = (x > pre) ? x : pre;
+  return (xm > limit) ? __hmul(two, hexp(__hneg(xm))) : __hneg(hlog(htanh(__hmul(xm, half_one))));
+}
+
+__global__ void build_phi_table_kernel(uint16_t *table) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kPhiTableSize) table[i] = __half_as_ushort(phi_abs_f16_exact(__ushort_as_half(uint16_t(i))));
+}
+
+__global__ void phi_abs_f32_kernel(const float *x, float *y, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = phi_abs_f32(x[i]);
+}
+
+template <class Tr> __device__ __forceinline__ const uint16_t *stage_phi_table(const uint16_t *g_table) {
+  if (Tr::kUsesTable) {
+    extern __shared__ __align__(16) uint16_t s_table[];
+    const uint4 *src = reinterpret_cast<const uint4 *>(g_table);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_table);
+    for (int i = threadIdx.x; i < kPhiTableSize * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+    return s_table;
+  }
+  return nullptr;
+}
+
+__device__ __forceinline__ uint32_t &word(uint4 &v, int i) { return reinterpret_cast<uint32_t *>(&v)[i]; }
+__device__ __forceinline__ uint32_t word(const uint4 &v, int i) { return reinterpret_cast<const uint32_t *>(&v)[i]; }
+
+// bits of this thread's frames out of a bit-sliced row (row_bytes = &row[0] as bytes)
+template <class Tr> __device__ __forceinline__ uint32_t load_frame_bits(const uint8_t *row_bytes, uint32_t g) {
+  if (Tr::kFramesPerVec == 8) return row_bytes[g];
+  return (row_bytes[g >> 1] >> ((g & 1u) * 4u)) & 0xFu;
+}
+
+// ---------------------------------------------------------------- check-node pass
+// One thread = (check c, frame vector g).  S = sum |m_e|; every edge gets phi_abs(S - |m_e|) with
+// sign = sign(m_e) xor parity, parity = syndrome bit xor (number of non-negative inputs) (flood.cu:77-115).
+template <class Tr>
+__global__ void __launch_bounds__(kThreads)
+    cn_update_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
+                     const uint16_t *__restrict__ phi_table, uint32_t n_checks, uint32_t log2_g) {
+  const uint16_t *tab = stage_phi_table<Tr>(phi_table);
+  const uint32_t G = 1u << log2_g;
+  const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
+  const uint64_t total = uint64_t(n_checks) << log2_g;
+  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
+       item += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t c = uint32_t(item >> log2_g);
+    const uint32_t g = uint32_t(item) & (G - 1u);
+    const uint32_t a = __ldg(row_ptr + c), b = __ldg(row_ptr + c + 1);
+    const uint32_t deg = b - a;
+    uint4 *p = msg + (size_t(a) << log2_g) + g;
+    const uint32_t sbits = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
+    // parity seed: syndrome bit xor (deg & 1); xor-ing the raw sign bits of all inputs then gives
+    // syndrome ^ #(non-negative inputs)
+    const uint32_t odd = (deg & 1u) ? Tr::kSignMask : 0u;
+    uint4 S = make_uint4(0, 0, 0, 0), X;
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      word(X, w) = Tr::sign_from_bits(sbits >> (w * Tr::kFramesPerWord)) ^ odd;
+    if (deg <= kMaxRegDeg) {
+      uint4 m[kMaxRegDeg];
+#pragma unroll
+      for (int k = 0; k < kMaxRegDeg; ++k)
+        if (k < deg) m[k] = ld_stream(p + (size_t(k) << log2_g));
+#pragma unroll
+      for (int k = 0; k < kMaxRegDeg; ++k)
+        if (k < deg) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            word(S, w) = Tr::add_w(word(S, w), Tr::abs_w(word(m[k], w)));
+            word(X, w) ^= word(m[k], w);
+          }
+        }
+#pragma unroll
+      for (int k = 0; k < kMaxRegDeg; ++k)
+        if (k < deg) {
+          uint4 o;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t mw = word(m[k], w);
+            const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab);
+            word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+          }
+          st_stream(p + (size_t(k) << log2_g), o);
+        }
+    } else {
+      for (uint32_t k = 0; k < deg; ++k) {
+        uint4 mk = ld_cached(p + (size_t(k) << log2_g));
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          word(S, w) = Tr::add_w(word(S, w), Tr::abs_w(word(mk, w)));
+          word(X, w) ^= word(mk, w);
+        }
+      }
+      for (uint32_t k = 0; k < deg; ++k) {
+        uint4 mk = ld_cached(p + (size_t(k) << log2_g));
+        uint4 o;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t mw = word(mk, w);
+          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab);
+          word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+        }
+        st_stream(p + (size_t(k) << log2_g), o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- variable-node pass
+// One thread = (variable v, frame vector g).  T = llr0 + sum of incoming c2v in CSC order; every edge gets
+// phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).
+template <class Tr, bool kFinalBits>
+__global__ void __launch_bounds__(kThreads)
+    vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ col_ptr,
+                     const uint32_t *__restrict__ in_to_out, uint8_t *__restrict__ hard,
+                     const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t log2_g) {
+  const uint16_t *tab = stage_phi_table<Tr>(phi_table);
+  const uint32_t G = 1u << log2_g;
+  const size_t hard_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
+  const uint64_t total = uint64_t(n_vars) << log2_g;
+  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
+       item += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t v = uint32_t(item >> log2_g);
+    const uint32_t g = uint32_t(item) & (G - 1u);
+    const uint32_t a = __ldg(col_ptr + v), b = __ldg(col_ptr + v + 1);
+    const uint32_t deg = b - a;
+    uint4 T = ld_stream(llr0 + (size_t(v) << log2_g) + g);
+    if (deg <= kMaxRegDeg) {
+      uint4 m[kMaxRegDeg];
+      uint4 *p[kMaxRegDeg];
+#pragma unroll
+      for (int k = 0; k < kMaxRegDeg; ++k)
+        if (k < deg) {
+          p[k] = msg + (size_t(__ldg(in_to_out + a + k)) << log2_g) + g;
+          m[k] = ld_stream(p[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < kMaxRegDeg; ++k)
+        if (k < deg) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) word(T, w) = Tr::add_w(word(T, w), word(m[k], w));
+        }
+#pragma unroll
+      for (int k = 0; k < kMaxRegDeg; ++k)
+        if (k < deg) {
+          uint4 o;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t pre = Tr::sub_w(word(T, w), word(m[k], w));
+            const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab);
+            word(o, w) = (r & ~Tr::kSignMask) | (pre & Tr::kSignMask);
+          }
+          st_stream(p[k], o);
+        }
+    } else {
+      for (uint32_t k = 0; k < deg; ++k) {
+        const uint4 mk = ld_cached(msg + (size_t(__ldg(in_to_out + a + k)) << log2_g) + g);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) word(T, w) = Tr::add_w(word(T, w), word(mk, w));
+      }
+      for (uint32_t k = 0; k < deg; ++k) {
+        uint4 *pk = msg + (size_t(__ldg(in_to_out + a + k)) << log2_g) + g;
+        const uint4 mk = ld_cached(pk);
+        uint4 o;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t pre = Tr::sub_w(word(T, w), word(mk, w));
+          const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab);
+          word(o, w) = (r & ~Tr::kSignMask) | (pre & Tr::kSignMask);
+        }
+        st_stream(pk, o);
+      }
+    }
+    if (kFinalBits) {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) bits |= Tr::hard_bits(word(T, w)) << (w * Tr::kFramesPerWord);
+      uint8_t *row = hard + size_t(v) * hard_row_bytes;
+      if (Tr::kFramesPerVec == 8) {
+        row[g] = uint8_t(bits);
+      } else {
+        // two neighbouring threads (g even/odd, same variable) share a byte
+        const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, bits, 1);
+        if ((g & 1u) == 0) row[g >> 1] = uint8_t(bits | (other << 4));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- syndrome check (bit-sliced)
+// One thread = (check c, 32-slot word w): x = syn[c][w] xor hard[var(e)][w] over the row; any set bit marks
+// that slot's frame as violated (flood.cu:191-223, 32 frames per XOR).
+__global__ void __launch_bounds__(kThreads)
+    syndrome_check_kernel(const uint32_t *__restrict__ syn, const uint32_t *__restrict__ hard,
+                          const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ edge_var,
+                          uint32_t *__restrict__ viol, uint32_t n_checks, uint32_t log2_pw) {
+  const uint32_t PW = 1u << log2_pw;
+  const uint64_t total = uint64_t(n_checks) << log2_pw;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x; // multiple of PW: a thread keeps its word w
+  uint32_t acc = 0;
+  const uint64_t first = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t w = uint32_t(first) & (PW - 1u);
+  for (uint64_t item = first; item < total; item += stride) {
+    const uint32_t c = uint32_t(item >> log2_pw);
+    const uint32_t a = __ldg(row_ptr + c), b = __ldg(row_ptr + c + 1);
+    uint32_t x = __ldg(syn + (size_t(c) << log2_pw) + w);
+    for (uint32_t e = a; e < b; ++e) x ^= __ldg(hard + (size_t(__ldg(edge_var + e)) << log2_pw) + w);
+    acc |= x;
+  }
+  if (acc) atomicOr(viol + w, acc);
+}
+
+// ---------------------------------------------------------------- refill of freed slots
+struct RefillEntry {     // one new frame
+  uint64_t src_offset;   // element offset of its first channel value in the staging/input array
+  uint64_t src_stride;   // element stride between consecutive variables
+  uint64_t syn_offset;   // u32 offset of its packed syndrome (frame-major, S words)
+  uint32_t slot;         // destination slot
+  uint32_t pad;
+};
+
+// One thread = (variable i, new frame t), t fastest: prior = llr(channel value) (0 for punctured variables),
+// and phi(prior) goes to every edge of the variable (flood.cu:47-75, 297-323).
+template <class Tr, typename Elem>
+__global__ void __launch_bounds__(kThreads)
+    refill_kernel(Elem *__restrict__ msg, Elem *__restrict__ llr0, const Elem *__restrict__ src,
+                  const RefillEntry *__restrict__ entries, uint32_t n_new, const uint32_t *__restrict__ col_ptr,
+                  const uint32_t *__restrict__ in_to_out, const uint16_t *__restrict__ phi_table, uint32_t n_vars,
+                  uint32_t n_regular, uint32_t log2_p, int channel, float param) {
+  const uint64_t total = uint64_t(n_vars) * n_new;
+  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
+       item += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t i = uint32_t(item / n_new);
+    const uint32_t t = uint32_t(item - uint64_t(i) * n_new);
+    const RefillEntry en = entries[t];
+    Elem llr, out;
+    if (sizeof(Elem) == 4) {
+      uint32_t raw = 0;
+      if (i < n_regular) raw = TraitsF32::to_llr(reinterpret_cast<const uint32_t *>(src)[en.src_offset + uint64_t(i) * en.src_stride], channel, param);
+      const uint32_t r = __float_as_uint(phi_abs_f32(__uint_as_float(raw & 0x7FFFFFFFu)));
+      const uint32_t o = (r & 0x7FFFFFFFu) | (raw & 0x80000000u);
+      llr = *reinterpret_cast<const Elem *>(&raw);
+      out = *reinterpret_cast<const Elem *>(&o);
+    } else {
+      uint16_t raw = 0;
+      if (i < n_regular) raw = TraitsF16::to_llr(reinterpret_cast<const uint16_t *>(src)[en.src_offset + uint64_t(i) * en.src_stride], channel, param);
+      const uint16_t r = __ldg(phi_table + (raw & 0x7FFFu));
+      const uint16_t o = uint16_t((r & 0x7FFFu) | (raw & 0x8000u));
+      llr = *reinterpret_cast<const Elem *>(&raw);
+      out = *reinterpret_cast<const Elem *>(&o);
+    }
+    llr0[(size_t(i) << log2_p) + en.slot] = llr;
+    const uint32_t a = __ldg(col_ptr + i), b = __ldg(col_ptr + i + 1);
+    for (uint32_t ie = a; ie < b; ++ie) msg[(size_t(__ldg(in_to_out + ie)) << log2_p) + en.slot] = out;
+  }
+}
+
+// One thread = (check c, slot word w) for words that received new frames: replace those slots' target bits.
+__global__ void __launch_bounds__(kThreads)
+    refill_syndrome_kernel(uint32_t *__restrict__ syn, const uint32_t *__restrict__ src_syn,
+                           const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ new_mask,
+                           const uint32_t *__restrict__ slot_entry, uint32_t n_checks, uint32_t log2_pw) {
+  const uint32_t PW = 1u << log2_pw;
+  const uint64_t total = uint64_t(n_checks) << log2_pw;
+  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
+       item += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t c = uint32_t(item >> log2_pw);
+    const uint32_t w = uint32_t(item) & (PW - 1u);
+    uint32_t mask = __ldg(new_mask + w);
+    if (!mask) continue;
+    uint32_t x = syn[(size_t(c) << log2_pw) + w] & ~mask;
+    while (mask) {
+      const uint32_t bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const RefillEntry en = entries[slot_entry[w * 32 + bit]];
+      x |= ((__ldg(src_syn + en.syn_offset + (c >> 5)) >> (c & 31u)) & 1u) << bit;
+    }
+    syn[(size_t(c) << log2_pw) + w] = x;
+  }
+}
+
+// ---------------------------------------------------------------- extraction of retired frames
+// One warp = (slot word w, tile of 32 result words).  Lane i reads hard[32j+i][w]; a ballot per retiring
+// slot of that word assembles result word j for that slot's frame; each warp then writes 128 B per frame
+// (LSB-first packing as flood.cu:277-295, but only for slots that actually retire).
+struct ExtractEntry {
+  uint64_t dst_offset; // u32 offset of the frame's packed result
+};
+
+__global__ void __launch_bounds__(128)
+    extract_kernel(const uint32_t *__restrict__ hard, uint32_t *__restrict__ dst, const uint32_t *__restrict__ retire_mask,
+                   const ExtractEntry *__restrict__ slot_dst, uint32_t n_words /* N/32 */, uint32_t log2_pw) {
+  __shared__ uint32_t s_out[4][32][33];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t PW = 1u << log2_pw;
+  const uint32_t n_tiles = (n_words + 31u) >> 5;
+  const uint64_t total = uint64_t(n_tiles) << log2_pw;
+  for (uint64_t wi = uint64_t(blockIdx.x) * 4 + warp; wi < total; wi += uint64_t(gridDim.x) * 4) {
+    const uint32_t w = uint32_t(wi) & (PW - 1u);
+    const uint32_t tile = uint32_t(wi >> log2_pw);
+    const uint32_t mask = __ldg(retire_mask + w);
+    if (!mask) continue; // warp-uniform
+    const uint32_t j0 = tile << 5;
+    const uint32_t jn = min(32u, n_words - j0);
+    for (uint32_t jj = 0; jj < jn; ++jj) {
+      const uint32_t x = __ldg(hard + ((size_t(j0 + jj) * 32 + lane) << log2_pw) + w);
+      uint32_t mm = mask, k = 0;
+      while (mm) {
+        const uint32_t bit = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const uint32_t r = __ballot_sync(0xFFFFFFFFu, (x >> bit) & 1u);
+        if (lane == 0) s_out[warp][k][jj] = r;
+        ++k;
+      }
+    }
+    __syncwarp();
+    uint32_t mm = mask, k = 0;
+    while (mm) {
+      const uint32_t bit = __ffs(mm) - 1;
+      mm &= mm - 1;
+      if (lane < jn) dst[slot_dst[w * 32 + bit].dst_offset + j0 + lane] = s_out[warp][k][lane];
+      ++k;
+    }
+    __syncwarp();
+  }
+}
+
+// gather one slot's column of a [rows][P] array (debug read-back)
+template <typename Elem>
+__global__ void gather_slot_kernel(const Elem *__restrict__ src, Elem *__restrict__ dst, uint64_t rows, uint32_t log2_p,
+                                   uint32_t slot) {
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < rows) dst[i] = src[(i << log2_p) + slot];
+}
+
+} // namespace dev
+} // namespace ldpc_b200

