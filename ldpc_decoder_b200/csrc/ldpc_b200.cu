@@ -578,6 +578,12 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   const bool simd_pairs = (prm->flags & LDPC_B200_FLAG_SIMD_PAIRS) != 0;
   const uint32_t B = std::min(n_frames, d->frames_in_flight); // num_vectors_gpu_batch
   const uint32_t k_check = prm->num_iter_check_parity;
+  // even-count refills can never load an odd remainder (the reference's OpenCL harness only ever feeds
+  // parallel_factor * loading_factor frames, ldpc_decoder_gpu.cpp:623 / main.cpp:320)
+  if (simd_pairs && ((n_frames - B) & 1u))
+    return fail(LDPC_B200_ERR_INVALID, "SIMD_PAIRS needs an even number of frames beyond the first batch");
+  // no frame may stay longer than num_iter_max + one check period, so this bounds the whole run
+  const uint64_t g_limit = (uint64_t(n_frames) / B + 2) * (uint64_t(prm->num_iter_max) + 2ull * k_check + 2);
 
   // position j of the reference's slot order -> (frame id, physical slot).  The reference physically
   // permutes frames (flood_permute_vecs); here only this table is permuted.
@@ -679,6 +685,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     }
     CU_TRY(cudaGetLastError());
     ++g;
+    if (g > g_limit) return fail(LDPC_B200_ERR_INVALID, "scheduler made no progress (internal error)");
   }
   CU_TRY(cudaEventRecord(ev_last, d->stream));
   CU_TRY(cudaStreamSynchronize(d->stream));
