@@ -107,8 +107,10 @@ typedef struct ldpc_b200_decode_params {
 } ldpc_b200_decode_params;
 
 enum {
-  LDPC_B200_FLAG_SIMD_PAIRS = 1u /* refill counts rounded down to even, as the reference's OpenCL *
-                                  * backend does (ldpc_decoder_gpu.cpp:623)                       */
+  LDPC_B200_FLAG_SIMD_PAIRS = 1u,  /* refill counts rounded down to even, as the reference's OpenCL *
+                                    * backend does (ldpc_decoder_gpu.cpp:623)                       */
+  LDPC_B200_FLAG_TIME_KERNELS = 2u /* bracket every check-node / variable-node launch with CUDA    *
+                                    * events on the launching stream and report cn_s / vn_s        */
 };
 
 typedef struct ldpc_b200_report {

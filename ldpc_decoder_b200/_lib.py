@@ -15,6 +15,7 @@ FP32, FP16 = 0, 1
 AWGN, BSC, LLR = 0, 1, 2
 LAYOUT_INTERLEAVED, LAYOUT_FRAME_MAJOR = 0, 1
 FLAG_SIMD_PAIRS = 1
+FLAG_TIME_KERNELS = 2
 
 
 class CodeInfo(C.Structure):

@@ -613,24 +613,49 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   rep.other_launches += 2;
   CU_TRY(cudaGetLastError());
 
+  // optional per-launch timing: events e[3i], e[3i+1], e[3i+2] bracket CN and VN of iteration i of a check period
+  const bool time_kernels = (prm->flags & LDPC_B200_FLAG_TIME_KERNELS) != 0;
+  struct event_pool {
+    std::vector<cudaEvent_t> ev;
+    ~event_pool() {
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+  } tev;
+  if (time_kernels) {
+    tev.ev.resize(3 * size_t(k_check + 1));
+    for (cudaEvent_t &e : tev.ev) CU_TRY(cudaEventCreate(&e));
+  }
+  uint32_t timed_iters = 0;
+  auto flush_timing = [&]() {
+    for (uint32_t i = 0; i < timed_iters; ++i) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, tev.ev[3 * i], tev.ev[3 * i + 1]);
+      cudaEventElapsedTime(&b, tev.ev[3 * i + 1], tev.ev[3 * i + 2]);
+      rep.cn_s += a * 1e-3;
+      rep.vn_s += b * 1e-3;
+    }
+    timed_iters = 0;
+  };
+
   uint32_t next_to_load = B, g = 0;
   double t_iter0 = now_s(), t_iter1 = t_iter0;
   for (;;) {
+    const bool check = g > 0 && (g % k_check) == 0; // :350
+    if (time_kernels) cudaEventRecord(tev.ev[3 * timed_iters], d->stream);
     d->launch_cn();
     rep.cn_launches++;
-    const bool check = g > 0 && (g % k_check) == 0; // :350
-    if (!check) {
-      d->launch_vn(false);
-      rep.vn_launches++;
-    } else {
-      d->launch_vn(true);
-      rep.vn_launches++;
+    if (time_kernels) cudaEventRecord(tev.ev[3 * timed_iters + 1], d->stream);
+    d->launch_vn(check);
+    rep.vn_launches++;
+    if (time_kernels) cudaEventRecord(tev.ev[3 * timed_iters + 2], d->stream), ++timed_iters;
+    if (check) {
       d->launch_check();
       rep.other_launches++;
       rep.n_checks_run++;
       CU_TRY(cudaMemcpyAsync(d->h_viol.p, d->d_viol.p, sizeof(uint32_t) << d->log2PW, cudaMemcpyDeviceToHost,
                              d->stream));
       CU_TRY(cudaStreamSynchronize(d->stream));
+      if (time_kernels) flush_timing();
       rep.d2h_bytes += sizeof(uint32_t) << d->log2PW;
       uint32_t n_stop = 0;
       for (uint32_t j = 0; j < B; ++j) { // stop rule, :395-403
