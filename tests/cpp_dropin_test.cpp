@@ -1,0 +1,53 @@
+// C++14 caller written against the drop-in class (what the reference's do_test does, main.cpp:315-441):
+// construct from an alist file + channel, ask parallel_factor(), decode, count errors.
+#include "../ldpc_decoder_b200/csrc/ldpc_decoder_gpu.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+using namespace ldpc_b200;
+
+int main(int argc, char **argv) {
+  if (argc < 2) return 2;
+  try {
+    ldpc_code code(argv[1]);
+    const float sigma = argc > 2 ? float(atof(argv[2])) : 0.6f;
+    biawgn_channel channel(sigma);
+    ldpc_decoder_gpu_static_parameters sp;
+    sp.m_max_log_parallel_factor_user = 4;
+    ldpc_decoder_gpu dec(code, channel, sp);
+    ldpc_decoder_gpu_dynamic_parameters dp;
+    dp.m_num_iter_max = 60;
+    const uint32_t n = dec.parallel_factor() * 3 + 5;
+    const int64_t N = code.n_inputs(), n_tx = N - code.n_erased_inputs(), S = (code.n_outputs() + 31) >> 5, W = N >> 5;
+    std::mt19937 rng(7);
+    std::normal_distribution<float> gauss(0.f, sigma);
+    std::vector<uint32_t> bits(size_t(n) * W), syn(size_t(n) * S), res(size_t(n) * W);
+    std::vector<float> input(size_t(N) * n, 0.f);
+    for (uint32_t v = 0; v < n; ++v) {
+      for (int64_t w = 0; w < W; ++w) bits[size_t(v) * W + w] = rng();
+      compute_syndrome(code, &bits[size_t(v) * W], &syn[size_t(v) * S]);
+      for (int64_t i = 0; i < n_tx; ++i)
+        input[size_t(v) + size_t(n) * i] = bool_to_llr((bits[size_t(v) * W + (i >> 5)] >> (i & 31)) & 1) + gauss(rng);
+    }
+    test_report report;
+    if (dec.decoding_input_is_llr()) return 3;
+    dec.decode(dp, n, input.data(), syn.data(), res.data(), report);
+    uint64_t errors = 0;
+    for (size_t i = 0; i < res.size(); ++i) errors += uint64_t(__builtin_popcount(res[i] ^ bits[i]));
+    std::printf("frames %u errors %llu iter max/min/avg %u/%u/%.3f\n", n, (unsigned long long)errors, report.max_iter,
+                report.min_iter, report.avg_iter);
+    // malformed input must surface as the reference's exception type
+    try {
+      ldpc_code bad("/nonexistent.alist");
+      return 4;
+    } catch (const error &) {
+    }
+    return errors == 0 ? 0 : 1;
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 5;
+  }
+}

@@ -310,3 +310,19 @@ def test_full_size_round_trip():
     assert conv.mean() > 0.9
     assert np.array_equal(gen.syndrome_packed(res[conv]), syn[conv])
     assert harness.count_bit_errors(res, bits)[conv].sum() == 0
+
+
+def test_cpp_dropin_class_decodes(small_codes, tmp_path):
+    """C++14 caller using the header-compatible class (constructor, parallel_factor, decode, test_report)."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = str(tmp_path / "cpp_dropin_test")
+    libdir = os.path.join(ROOT, "ldpc_decoder_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", os.path.join(ROOT, "tests", "cpp_dropin_test.cpp"), "-o", exe,
+                           "-L" + libdir, "-lldpc_b200", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe, small_codes["readme13"][1], "0.55"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "errors 0" in r.stdout

@@ -149,3 +149,17 @@ def test_oracle_kernel_steps_equal_its_decode(small_codes):
             break
     assert it < 29
     assert np.array_equal(dec.deinterlace(), bits)
+
+
+def test_cpp_dropin_class_compiles_and_reports_errors(tmp_path):
+    """The C++14 caller in tests/cpp_dropin_test.cpp builds against the drop-in header with -std=c++14 and the
+    reference's exception type comes back for an unreadable alist (no GPU needed for that path)."""
+    import subprocess
+
+    exe = str(tmp_path / "cpp_dropin_test")
+    libdir = os.path.join(ROOT, "ldpc_decoder_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(ROOT, "tests", "cpp_dropin_test.cpp"), "-o", exe, "-L" + libdir, "-lldpc_b200",
+                           "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe, "/nonexistent.alist"], capture_output=True, text=True)
+    assert r.returncode == 5 and "could not be opened" in r.stderr
