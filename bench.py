@@ -294,6 +294,8 @@ def main():
         "cn": {"gbs": cn_gbs, "frac": cn_gbs / peak, "avg_ms": 1e3 * cn_s / n_cn, "bytes_per_launch": cn_bytes},
         "vn": {"gbs": vn_gbs, "frac": vn_gbs / peak, "avg_ms": 1e3 * vn_s / n_vn, "bytes_per_launch": vn_bytes},
         "kernel_share_of_step": (cn_s + vn_s) / dev_s if dev_s else None,
+        "service_s_per_step": {k: sum(r[k] for r in reps) / len(reps) for k in ("check_s", "retire_s", "refill_s")},
+        "frames_refilled_per_step": sum(r["frames_refilled"] for r in reps) / len(reps),
     }
 
     # e2e: same call with host buffers

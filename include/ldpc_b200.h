@@ -124,6 +124,11 @@ typedef struct ldpc_b200_report {
   double cn_s, vn_s;           /* accumulated CUDA-event time of the CN / VN kernels         */
   uint64_t cn_launches, vn_launches, other_launches;
   uint64_t h2d_bytes, d2h_bytes;
+  /* LDPC_B200_FLAG_TIME_KERNELS only: host wall time (stream-synchronised) of the per-check service steps */
+  double check_s;  /* syndrome check kernel + flag read-back                         */
+  double retire_s; /* extraction of retiring frames (+ D2H when results are on host) */
+  double refill_s; /* staging (+ H2D) and refill kernels of new frames               */
+  uint64_t frames_refilled;
 } ldpc_b200_report;
 
 /* decode() (ldpc_decoder_gpu.h:102-110; semantics of ldpc_decoder_gpu.cu:283-634).

@@ -40,7 +40,9 @@ class Report(C.Structure):
                 ("iter_time_per_vector", C.c_float), ("global_iters", C.c_uint32), ("n_checks_run", C.c_uint32),
                 ("elapsed_s", C.c_double), ("device_s", C.c_double), ("cn_s", C.c_double), ("vn_s", C.c_double),
                 ("cn_launches", C.c_uint64), ("vn_launches", C.c_uint64), ("other_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("check_s", C.c_double), ("retire_s", C.c_double), ("refill_s", C.c_double),
+                ("frames_refilled", C.c_uint64)]
 
 
 # every symbol include/ldpc_b200.h declares: name -> (restype, argtypes)

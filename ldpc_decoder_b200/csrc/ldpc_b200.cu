@@ -649,13 +649,21 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     rep.vn_launches++;
     if (time_kernels) cudaEventRecord(tev.ev[3 * timed_iters + 2], d->stream), ++timed_iters;
     if (check) {
+      double t_svc = 0;
+      if (time_kernels) {
+        cudaStreamSynchronize(d->stream);
+        t_svc = now_s();
+      }
       d->launch_check();
       rep.other_launches++;
       rep.n_checks_run++;
       CU_TRY(cudaMemcpyAsync(d->h_viol.p, d->d_viol.p, sizeof(uint32_t) << d->log2PW, cudaMemcpyDeviceToHost,
                              d->stream));
       CU_TRY(cudaStreamSynchronize(d->stream));
-      if (time_kernels) flush_timing();
+      if (time_kernels) {
+        flush_timing();
+        rep.check_s += now_s() - t_svc;
+      }
       rep.d2h_bytes += sizeof(uint32_t) << d->log2PW;
       uint32_t n_stop = 0;
       for (uint32_t j = 0; j < B; ++j) { // stop rule, :395-403
@@ -695,12 +703,23 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
           tmp_slots[j] = virt[j];
           tmp_frames[j] = in_gpu[j];
         }
+        if (time_kernels) t_svc = now_s();
         st = retire_frames(d, n_new, tmp_slots.data(), tmp_frames.data(), results, results_on_device, &rep);
         if (st != LDPC_B200_OK) return st;
+        if (time_kernels) {
+          cudaStreamSynchronize(d->stream);
+          rep.retire_s += now_s() - t_svc;
+          t_svc = now_s();
+        }
         st = stage_frames(d, in, next_to_load, n_new, tmp_slots.data(), &src_dev, &syn_dev, &rep);
         if (st != LDPC_B200_OK) return st;
         d->launch_refill(n_new, src_dev, syn_dev, prm->channel, prm->channel_param);
         rep.other_launches += 3;
+        rep.frames_refilled += n_new;
+        if (time_kernels) {
+          cudaStreamSynchronize(d->stream);
+          rep.refill_s += now_s() - t_svc;
+        }
         for (uint32_t j = 0; j < n_new; ++j) { // :604-609
           in_gpu[j] = next_to_load + j;
           iter_start[next_to_load + j] = g;
