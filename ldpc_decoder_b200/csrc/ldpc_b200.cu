@@ -191,6 +191,14 @@ struct ldpc_b200_decoder {
   dev_buf<dev::RefillEntry> d_refill;
   dev_buf<dev::ExtractEntry> d_extract;
   dev_buf<uint16_t> d_phi_table;
+  // device-resident scheduler state (dev::sched_kernel)
+  dev_buf<dev::SchedState> d_state;
+  dev_buf<dev::SchedSummary> d_summary;
+  dev_buf<uint32_t> d_n_new, d_in_gpu, d_virt, d_retired, d_iter; // d_iter: [2][n_frames] start/end, grown on demand
+  pinned_buf<dev::SchedSummary> h_summary; // [2]
+  pinned_buf<uint32_t> h_retired;          // [2][P]
+  cudaStream_t copy_stream = nullptr;      // H2D of new frames / D2H of results, overlapped with decoding
+  cudaEvent_t ev_staged = nullptr, ev_refilled = nullptr, ev_period[2] = {nullptr, nullptr}, ev_extracted[2] = {nullptr, nullptr};
   pinned_buf<uint8_t> h_stage;
   pinned_buf<uint32_t> h_stage_syn, h_viol, h_results, h_mask, h_retire_mask, h_slot_entry;
   pinned_buf<dev::RefillEntry> h_refill;
@@ -202,20 +210,23 @@ struct ldpc_b200_decoder {
   size_t smem_tab = 0;
 
   ~ldpc_b200_decoder() {
-    if (ev_a) cudaEventDestroy(ev_a);
-    if (ev_b) cudaEventDestroy(ev_b);
+    for (cudaEvent_t e : {ev_a, ev_b, ev_staged, ev_refilled, ev_period[0], ev_period[1], ev_extracted[0], ev_extracted[1]})
+      if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
+  const uint32_t *done_flag() const { return &d_state.p->done; }
 
   // ---- launches -----------------------------------------------------------
   void launch_cn() {
     if (precision == LDPC_B200_FP32)
       dev::cn_update_kernel<dev::TraitsF32><<<grid_cn, dev::kThreads, 0, stream>>>(
-          reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), nullptr, M, log2G);
+          reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), nullptr, M, log2G,
+          done_flag());
     else
       dev::cn_update_kernel<dev::TraitsF16><<<grid_cn, dev::kThreads, smem_tab, stream>>>(
           reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p, M,
-          log2G);
+          log2G, done_flag());
   }
   void launch_vn(bool bits) {
     uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p);
@@ -224,27 +235,41 @@ struct ldpc_b200_decoder {
     if (precision == LDPC_B200_FP32) {
       if (bits)
         dev::vn_update_kernel<dev::TraitsF32, true><<<grid_vnb, dev::kThreads, 0, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G);
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G, done_flag());
       else
         dev::vn_update_kernel<dev::TraitsF32, false><<<grid_vn, dev::kThreads, 0, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G);
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G, done_flag());
     } else {
       if (bits)
         dev::vn_update_kernel<dev::TraitsF16, true><<<grid_vnb, dev::kThreads, smem_tab, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G);
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G, done_flag());
       else
         dev::vn_update_kernel<dev::TraitsF16, false><<<grid_vn, dev::kThreads, smem_tab, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G);
+            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G, done_flag());
     }
   }
   void launch_check() {
     cudaMemsetAsync(d_viol.p, 0, sizeof(uint32_t) << log2PW, stream);
     dev::syndrome_check_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, d_hard.p, d_row_ptr.p, d_edge_var.p,
-                                                                        d_viol.p, M, log2PW);
+                                                                        d_viol.p, M, log2PW, done_flag());
   }
-  // entries (h_refill[0..n)) -> device, then scatter priors, first messages and syndromes
+  // refill kernels: entries, count, masks are already in device memory (scheduler kernel or host upload)
+  void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param) {
+    const uint32_t n_regular = N - n_erased;
+    if (precision == LDPC_B200_FP32)
+      dev::refill_kernel<dev::TraitsF32, float><<<grid_misc, dev::kThreads, 0, stream>>>(
+          reinterpret_cast<float *>(d_msg.p), reinterpret_cast<float *>(d_llr0.p), static_cast<const float *>(src),
+          d_refill.p, d_n_new.p, d_col_ptr.p, d_in_to_out.p, nullptr, N, n_regular, log2P, channel, param);
+    else
+      dev::refill_kernel<dev::TraitsF16, uint16_t><<<grid_misc, dev::kThreads, 0, stream>>>(
+          reinterpret_cast<uint16_t *>(d_msg.p), reinterpret_cast<uint16_t *>(d_llr0.p),
+          static_cast<const uint16_t *>(src), d_refill.p, d_n_new.p, d_col_ptr.p, d_in_to_out.p, d_phi_table.p, N,
+          n_regular, log2P, channel, param);
+    dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
+                                                                         d_new_mask.p, d_slot_entry.p, M, log2PW);
+  }
+  // host-built entries (kernel-level entry points): h_refill[0..n) -> device, then the same kernels
   void launch_refill(uint32_t n_new, const void *src, const uint32_t *src_syn, int channel, float param) {
-    // slot masks / entry index per slot
     const uint32_t PW = 1u << log2PW;
     std::fill(h_mask.p, h_mask.p + PW, 0u);
     for (uint32_t t = 0; t < n_new; ++t) {
@@ -252,27 +277,21 @@ struct ldpc_b200_decoder {
       h_mask.p[s >> 5] |= 1u << (s & 31);
       h_slot_entry.p[s] = t;
     }
+    h_viol.p[0] = n_new; // pinned scratch word
+    cudaMemcpyAsync(d_n_new.p, h_viol.p, sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_refill.p, h_refill.p, sizeof(dev::RefillEntry) * n_new, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_new_mask.p, h_mask.p, sizeof(uint32_t) * PW, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_slot_entry.p, h_slot_entry.p, sizeof(uint32_t) * P, cudaMemcpyHostToDevice, stream);
-    const uint32_t n_regular = N - n_erased;
-    if (precision == LDPC_B200_FP32)
-      dev::refill_kernel<dev::TraitsF32, float><<<grid_misc, dev::kThreads, 0, stream>>>(
-          reinterpret_cast<float *>(d_msg.p), reinterpret_cast<float *>(d_llr0.p), static_cast<const float *>(src),
-          d_refill.p, n_new, d_col_ptr.p, d_in_to_out.p, nullptr, N, n_regular, log2P, channel, param);
-    else
-      dev::refill_kernel<dev::TraitsF16, uint16_t><<<grid_misc, dev::kThreads, 0, stream>>>(
-          reinterpret_cast<uint16_t *>(d_msg.p), reinterpret_cast<uint16_t *>(d_llr0.p),
-          static_cast<const uint16_t *>(src), d_refill.p, n_new, d_col_ptr.p, d_in_to_out.p, d_phi_table.p, N,
-          n_regular, log2P, channel, param);
-    dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_new_mask.p,
-                                                                         d_slot_entry.p, M, log2PW);
+    launch_refill_kernels(src, src_syn, channel, param);
   }
   // h_extract[slot].dst_offset valid for every slot set in h_retire_mask
   void launch_extract(uint32_t *dst) {
     const uint32_t PW = 1u << log2PW;
     cudaMemcpyAsync(d_retire_mask.p, h_retire_mask.p, sizeof(uint32_t) * PW, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_extract.p, h_extract.p, sizeof(dev::ExtractEntry) * P, cudaMemcpyHostToDevice, stream);
+    launch_extract_kernel(dst);
+  }
+  void launch_extract_kernel(uint32_t *dst) { // masks and destinations already on the device
     dev::extract_kernel<<<grid_misc, 128, 0, stream>>>(d_hard.p, dst, d_retire_mask.p, d_extract.p, W, log2PW);
   }
 };
@@ -371,6 +390,15 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   CU_TRY(d->d_refill.alloc(P));
   CU_TRY(d->d_extract.alloc(P));
   CU_TRY(d->d_phi_table.alloc(dev::kPhiTableSize));
+  CU_TRY(d->d_state.alloc(1));
+  CU_TRY(d->d_summary.alloc(1));
+  CU_TRY(d->d_n_new.alloc(1));
+  CU_TRY(d->d_in_gpu.alloc(P));
+  CU_TRY(d->d_virt.alloc(P));
+  CU_TRY(d->d_retired.alloc(P));
+  CU_TRY(cudaMemset(d->d_state.p, 0, sizeof(dev::SchedState)));
+  CU_TRY(d->h_summary.alloc(2));
+  CU_TRY(d->h_retired.alloc(2 * P));
   CU_TRY(cudaMemset(d->d_msg.p, 0, size_t(d->E) * P * d->elem));
   CU_TRY(cudaMemset(d->d_llr0.p, 0, size_t(d->N) * P * d->elem));
   CU_TRY(cudaMemset(d->d_syn.p, 0, (size_t(d->M) << d->log2PW) * 4));
@@ -385,6 +413,13 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   CU_TRY(d->h_refill.alloc(P));
   CU_TRY(d->h_extract.alloc(P));
   CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&d->ev_staged, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&d->ev_refilled, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_period[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_extracted[i], cudaEventDisableTiming));
+  }
   CU_TRY(cudaEventCreate(&d->ev_a));
   CU_TRY(cudaEventCreate(&d->ev_b));
 
@@ -554,6 +589,12 @@ ldpc_b200_status retire_frames(ldpc_b200_decoder *d, uint32_t cnt, const uint32_
 
 extern "C" {
 
+// decode(): the reference's scheduling semantics (ldpc_decoder_gpu.cu:283-634) with the decisions taken on
+// the device.  Per check period the compute stream runs
+//     [CN, VN] x k  ->  syndrome check  ->  sched_kernel  ->  extract  ->  refill
+// without waiting for the host; the host only (a) keeps one period of work queued ahead, (b) stages the next
+// frames into a device ring over pinned cudaMemcpyAsync on the copy stream while the flood iterations run,
+// (c) drains retired frames' packed decisions on the copy stream, (d) watches the summary for the end.
 ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm, uint32_t n_frames,
                                   const void *input, const uint32_t *syndromes, uint32_t *results,
                                   ldpc_b200_report *report, uint32_t *iter_counts) {
@@ -566,32 +607,167 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   ldpc_b200_report rep;
   memset(&rep, 0, sizeof(rep));
 
-  input_view in;
-  in.base = static_cast<const uint8_t *>(input);
-  in.syn = syndromes;
-  in.on_device = is_device_pointer(input);
-  in.syn_on_device = is_device_pointer(syndromes);
-  in.layout = prm->input_layout;
-  in.frame_stride = prm->frame_stride ? prm->frame_stride : (d->N - d->n_erased);
-  in.n_cols = prm->input_pool_frames ? prm->input_pool_frames : n_frames;
-  const bool results_on_device = is_device_pointer(results);
+  const bool in_dev = is_device_pointer(input), syn_dev = is_device_pointer(syndromes);
+  const bool res_dev = is_device_pointer(results);
   const bool simd_pairs = (prm->flags & LDPC_B200_FLAG_SIMD_PAIRS) != 0;
+  const bool time_kernels = (prm->flags & LDPC_B200_FLAG_TIME_KERNELS) != 0;
   const uint32_t B = std::min(n_frames, d->frames_in_flight); // num_vectors_gpu_batch
   const uint32_t k_check = prm->num_iter_check_parity;
+  const uint32_t n_reg = d->N - d->n_erased;
+  const uint32_t n_cols = prm->input_pool_frames ? prm->input_pool_frames : n_frames;
+  const size_t es = d->elem;
   // even-count refills can never load an odd remainder (the reference's OpenCL harness only ever feeds
   // parallel_factor * loading_factor frames, ldpc_decoder_gpu.cpp:623 / main.cpp:320)
   if (simd_pairs && ((n_frames - B) & 1u))
     return fail(LDPC_B200_ERR_INVALID, "SIMD_PAIRS needs an even number of frames beyond the first batch");
   // no frame may stay longer than num_iter_max + one check period, so this bounds the whole run
-  const uint64_t g_limit = (uint64_t(n_frames) / B + 2) * (uint64_t(prm->num_iter_max) + 2ull * k_check + 2);
+  const uint64_t period_limit =
+      (uint64_t(n_frames) / B + 2) * ((uint64_t(prm->num_iter_max) + 2ull * k_check + 2) / k_check + 2);
 
-  // position j of the reference's slot order -> (frame id, physical slot).  The reference physically
-  // permutes frames (flood_permute_vecs); here only this table is permuted.
-  std::vector<uint32_t> in_gpu(B), virt(B);
-  std::vector<uint32_t> iter_start(n_frames, uint32_t(-1)), iter_end(n_frames, uint32_t(-1));
-  std::vector<uint8_t> stop(B);
-  std::vector<uint32_t> origin, dest, tmp_slots(B), tmp_frames(B);
-  for (uint32_t j = 0; j < B; ++j) in_gpu[j] = virt[j] = j;
+  // ---- scheduler constants
+  dev::SchedConst sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.n_frames = n_frames;
+  sc.batch = B;
+  sc.log2_p = d->log2P;
+  sc.k_check = k_check;
+  sc.imax = prm->num_iter_max;
+  sc.simd_pairs = simd_pairs;
+  sc.syn_words = d->S;
+  sc.res_words = d->W;
+  sc.n_cols = n_cols;
+  sc.n_regular = n_reg;
+  sc.frame_stride = prm->frame_stride ? prm->frame_stride : n_reg;
+  const bool frame_major = prm->input_layout == LDPC_B200_LAYOUT_FRAME_MAJOR;
+  const uint32_t ring_block = frame_major ? 1u : 32u; // frames per interleaved staging block (64-128 B runs)
+  // live staged frames are always inside [next_to_load, next_to_load + B) (+ block rounding)
+  const uint32_t ring_frames = std::min<uint32_t>(d->P, ((B + ring_block - 1) / ring_block + 1) * ring_block);
+  sc.ring_block = ring_block;
+  sc.ring_frames = ring_frames;
+  sc.input_mode = in_dev ? (frame_major ? 1u : 0u) : (frame_major ? 3u : 2u);
+  sc.syn_ring = syn_dev ? 0u : 1u;
+  sc.results_ring = res_dev ? 0u : 1u;
+  if (!in_dev && ring_frames < std::min<uint32_t>(d->P, B + ring_block) && ring_frames < B)
+    return fail(LDPC_B200_ERR_INVALID, "staging ring too small (internal error)");
+  const void *src_dev = in_dev ? input : static_cast<const void *>(d->d_stage.p);
+  const uint32_t *syn_src_dev = syn_dev ? syndromes : d->d_stage_syn.p;
+  uint32_t *res_dst_dev = res_dev ? results : d->d_results.p;
+
+  if (d->d_iter.n < 2ull * n_frames) CU_TRY(d->d_iter.alloc(2ull * n_frames));
+  uint32_t *d_iter_start = d->d_iter.p, *d_iter_end = d->d_iter.p + n_frames;
+
+  // ---- staging of host-resident frames into the device ring (copy stream)
+  // frames [staged, upto) are gathered by all host threads into pinned memory laid out like the ring, then
+  // copied block by block.  Ring position of frame f: f % ring_frames.
+  uint32_t staged = 0;
+  bool refill_recorded = false;
+  const uint8_t *in_host = static_cast<const uint8_t *>(input);
+  auto stage_upto = [&](uint32_t upto) -> ldpc_b200_status {
+    if (in_dev && syn_dev) return LDPC_B200_OK;
+    upto = std::min(n_frames, upto);
+    if (upto <= staged) return LDPC_B200_OK;
+    CU_TRY(cudaStreamSynchronize(d->copy_stream)); // earlier copies out of the pinned mirror are done
+    // ring positions being overwritten belong to frames already loaded; their refill kernels must have read them
+    if (refill_recorded) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_refilled, 0));
+    const uint32_t f0 = staged, f1 = upto;
+    if (!in_dev) {
+      if (!frame_major) {
+        // the reference's prepare_vectors (ldpc_decoder_gpu.cu:199-207) in blocks of ring_block frames:
+        // pinned[blk][i][0..ring_block) <- input[i][col..col+run)
+        parallel_for(n_reg, d->host_threads, [&](size_t ia, size_t ib) {
+          for (size_t i = ia; i < ib; ++i) {
+            const uint8_t *row = in_host + i * size_t(n_cols) * es;
+            uint32_t f = f0;
+            while (f < f1) {
+              const uint32_t r = f % ring_frames, in_blk = r % ring_block, col = f % n_cols;
+              const uint32_t run = std::min({f1 - f, ring_block - in_blk, n_cols - col});
+              uint8_t *dst = d->h_stage.p + ((size_t(r / ring_block) * n_reg + i) * ring_block + in_blk) * es;
+              memcpy(dst, row + size_t(col) * es, size_t(run) * es);
+              f += run;
+            }
+          }
+        });
+        // one H2D per touched block range (contiguous blocks in the ring)
+        uint32_t f = f0;
+        while (f < f1) {
+          const uint32_t r = f % ring_frames;
+          const uint32_t blk0 = r / ring_block;
+          const uint32_t run = std::min(f1 - f, ring_frames - blk0 * ring_block); // up to the end of the ring
+          const uint32_t n_blk = (r % ring_block + run + ring_block - 1) / ring_block;
+          const size_t off = size_t(blk0) * n_reg * ring_block * es, bytes = size_t(n_blk) * n_reg * ring_block * es;
+          CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
+          rep.h2d_bytes += bytes;
+          f += std::min(run, n_blk * ring_block - r % ring_block);
+        }
+      } else {
+        parallel_for(f1 - f0, d->host_threads, [&](size_t a, size_t b2) {
+          for (size_t t = a; t < b2; ++t) {
+            const uint32_t f = f0 + uint32_t(t);
+            memcpy(d->h_stage.p + size_t(f % ring_frames) * n_reg * es,
+                   in_host + size_t(f % n_cols) * sc.frame_stride * es, size_t(n_reg) * es);
+          }
+        });
+        uint32_t f = f0;
+        while (f < f1) {
+          const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
+          const size_t off = size_t(r) * n_reg * es, bytes = size_t(run) * n_reg * es;
+          CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
+          rep.h2d_bytes += bytes;
+          f += run;
+        }
+      }
+    }
+    if (!syn_dev) {
+      for (uint32_t f = f0; f < f1; ++f)
+        memcpy(d->h_stage_syn.p + size_t(f % ring_frames) * d->S, syndromes + size_t(f % n_cols) * d->S,
+               size_t(d->S) * 4);
+      uint32_t f = f0;
+      while (f < f1) {
+        const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
+        CU_TRY(cudaMemcpyAsync(d->d_stage_syn.p + size_t(r) * d->S, d->h_stage_syn.p + size_t(r) * d->S,
+                               size_t(run) * d->S * 4, cudaMemcpyHostToDevice, d->copy_stream));
+        rep.h2d_bytes += size_t(run) * d->S * 4;
+        f += run;
+      }
+    }
+    staged = f1;
+    CU_TRY(cudaEventRecord(d->ev_staged, d->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_staged, 0)); // the refill kernels read the ring
+    return LDPC_B200_OK;
+  };
+
+  // ---- optional per-launch timing: two event pools (periods alternate), 3 events per flood iteration
+  struct event_pool {
+    std::vector<cudaEvent_t> ev;
+    ~event_pool() {
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+  } tev[2], sev[2];
+  uint32_t timed_iters[2] = {0, 0};
+  if (time_kernels)
+    for (int h = 0; h < 2; ++h) {
+      tev[h].ev.resize(3 * size_t(k_check + 1));
+      sev[h].ev.resize(4);
+      for (cudaEvent_t &e : tev[h].ev) CU_TRY(cudaEventCreate(&e));
+      for (cudaEvent_t &e : sev[h].ev) CU_TRY(cudaEventCreate(&e));
+    }
+  auto flush_timing = [&](int h) {
+    for (uint32_t i = 0; i < timed_iters[h]; ++i) {
+      float a = 0, b2 = 0;
+      cudaEventElapsedTime(&a, tev[h].ev[3 * i], tev[h].ev[3 * i + 1]);
+      cudaEventElapsedTime(&b2, tev[h].ev[3 * i + 1], tev[h].ev[3 * i + 2]);
+      rep.cn_s += a * 1e-3;
+      rep.vn_s += b2 * 1e-3;
+    }
+    timed_iters[h] = 0;
+    float c1 = 0, c2 = 0, c3 = 0;
+    cudaEventElapsedTime(&c1, sev[h].ev[0], sev[h].ev[1]);
+    cudaEventElapsedTime(&c2, sev[h].ev[1], sev[h].ev[2]);
+    cudaEventElapsedTime(&c3, sev[h].ev[2], sev[h].ev[3]);
+    rep.check_s += c1 * 1e-3;
+    rep.retire_s += c2 * 1e-3;
+    rep.refill_s += c3 * 1e-3;
+  };
 
   cudaEvent_t ev_first, ev_last;
   CU_TRY(cudaEventCreate(&ev_first));
@@ -604,152 +780,128 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     }
   } guard{ev_first, ev_last};
 
-  const void *src_dev = nullptr;
-  const uint32_t *syn_dev = nullptr;
-  ldpc_b200_status st = stage_frames(d, in, 0, B, virt.data(), &src_dev, &syn_dev, &rep);
+  // ---- first batch: frames 0..B-1 into slots 0..B-1
+  ldpc_b200_status st = stage_upto(B);
   if (st != LDPC_B200_OK) return st;
   CU_TRY(cudaEventRecord(ev_first, d->stream));
-  d->launch_refill(B, src_dev, syn_dev, prm->channel, prm->channel_param);
-  rep.other_launches += 2;
+  dev::sched_init_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(sc, d->d_state.p, d->d_in_gpu.p, d->d_virt.p,
+                                                                  d_iter_start, d_iter_end, d->d_refill.p, d->d_n_new.p,
+                                                                  d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p);
+  d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param);
+  CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
+  refill_recorded = true;
+  rep.other_launches += 3;
   CU_TRY(cudaGetLastError());
 
-  // optional per-launch timing: events e[3i], e[3i+1], e[3i+2] bracket CN and VN of iteration i of a check period
-  const bool time_kernels = (prm->flags & LDPC_B200_FLAG_TIME_KERNELS) != 0;
-  struct event_pool {
-    std::vector<cudaEvent_t> ev;
-    ~event_pool() {
-      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  auto enqueue_iterations = [&](uint64_t period) {
+    const int h = int(period & 1);
+    const uint32_t n_it = period == 0 ? k_check + 1 : k_check; // g = 0..k, then k more per period (:350)
+    for (uint32_t i = 0; i < n_it; ++i) {
+      const bool last = i + 1 == n_it;
+      if (time_kernels) cudaEventRecord(tev[h].ev[3 * i], d->stream);
+      d->launch_cn();
+      if (time_kernels) cudaEventRecord(tev[h].ev[3 * i + 1], d->stream);
+      d->launch_vn(last);
+      if (time_kernels) cudaEventRecord(tev[h].ev[3 * i + 2], d->stream);
     }
-  } tev;
-  if (time_kernels) {
-    tev.ev.resize(3 * size_t(k_check + 1));
-    for (cudaEvent_t &e : tev.ev) CU_TRY(cudaEventCreate(&e));
-  }
-  uint32_t timed_iters = 0;
-  auto flush_timing = [&]() {
-    for (uint32_t i = 0; i < timed_iters; ++i) {
-      float a = 0, b = 0;
-      cudaEventElapsedTime(&a, tev.ev[3 * i], tev.ev[3 * i + 1]);
-      cudaEventElapsedTime(&b, tev.ev[3 * i + 1], tev.ev[3 * i + 2]);
-      rep.cn_s += a * 1e-3;
-      rep.vn_s += b * 1e-3;
-    }
-    timed_iters = 0;
+    if (time_kernels) timed_iters[h] = n_it;
+    rep.cn_launches += n_it;
+    rep.vn_launches += n_it;
+    if (time_kernels) cudaEventRecord(sev[h].ev[0], d->stream);
+    d->launch_check();
+    rep.other_launches++;
+    rep.n_checks_run++;
+    if (time_kernels) cudaEventRecord(sev[h].ev[1], d->stream);
+  };
+  auto enqueue_service = [&](uint64_t period) -> ldpc_b200_status {
+    const int h = int(period & 1);
+    dev::sched_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(
+        sc, d->d_state.p, d->d_viol.p, d->d_in_gpu.p, d->d_virt.p, d_iter_start, d_iter_end, d->d_refill.p,
+        d->d_extract.p, d->d_n_new.p, d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p, d->d_retired.p,
+        d->d_summary.p);
+    d->launch_extract_kernel(res_dst_dev);
+    if (time_kernels) cudaEventRecord(sev[h].ev[2], d->stream);
+    CU_TRY(cudaEventRecord(d->ev_extracted[h], d->stream));
+    d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param);
+    CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
+    if (time_kernels) cudaEventRecord(sev[h].ev[3], d->stream);
+    CU_TRY(cudaMemcpyAsync(d->h_summary.p + h, d->d_summary.p, sizeof(dev::SchedSummary), cudaMemcpyDeviceToHost,
+                           d->stream));
+    if (!res_dev)
+      CU_TRY(cudaMemcpyAsync(d->h_retired.p + size_t(h) * d->P, d->d_retired.p, sizeof(uint32_t) * B,
+                             cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaEventRecord(d->ev_period[h], d->stream));
+    rep.other_launches += 4;
+    return LDPC_B200_OK;
   };
 
-  uint32_t next_to_load = B, g = 0;
-  double t_iter0 = now_s(), t_iter1 = t_iter0;
+  // ---- main loop: the device is always one period ahead of the host
+  uint64_t period = 0;
+  uint32_t next_known = B; // next_to_load as of the last summary read
+  enqueue_iterations(0);
   for (;;) {
-    const bool check = g > 0 && (g % k_check) == 0; // :350
-    if (time_kernels) cudaEventRecord(tev.ev[3 * timed_iters], d->stream);
-    d->launch_cn();
-    rep.cn_launches++;
-    if (time_kernels) cudaEventRecord(tev.ev[3 * timed_iters + 1], d->stream);
-    d->launch_vn(check);
-    rep.vn_launches++;
-    if (time_kernels) cudaEventRecord(tev.ev[3 * timed_iters + 2], d->stream), ++timed_iters;
-    if (check) {
-      double t_svc = 0;
-      if (time_kernels) {
-        cudaStreamSynchronize(d->stream);
-        t_svc = now_s();
+    if (period > 0) {
+      const int hp = int((period - 1) & 1);
+      CU_TRY(cudaEventSynchronize(d->ev_period[hp])); // the host sleeps here while the next iterations run
+      if (time_kernels) flush_timing(hp);
+      const dev::SchedSummary sm = d->h_summary.p[hp];
+      rep.d2h_bytes += sizeof(dev::SchedSummary);
+      rep.frames_refilled += sm.n_new;
+      next_known = sm.next_to_load;
+      if (!res_dev && sm.n_retired) { // drain the result ring of period-1 on the copy stream
+        const size_t bytes = size_t(sm.n_retired) * d->W * 4;
+        CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_extracted[hp], 0));
+        CU_TRY(cudaMemcpyAsync(d->h_results.p, d->d_results.p, bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+        CU_TRY(cudaStreamSynchronize(d->copy_stream));
+        const uint32_t *frames = d->h_retired.p + size_t(hp) * d->P;
+        parallel_for(sm.n_retired, d->host_threads, [&](size_t a, size_t b2) {
+          for (size_t t = a; t < b2; ++t)
+            memcpy(results + size_t(frames[t]) * d->W, d->h_results.p + t * d->W, size_t(d->W) * 4);
+        });
+        rep.d2h_bytes += bytes + sizeof(uint32_t) * B;
       }
-      d->launch_check();
-      rep.other_launches++;
-      rep.n_checks_run++;
-      CU_TRY(cudaMemcpyAsync(d->h_viol.p, d->d_viol.p, sizeof(uint32_t) << d->log2PW, cudaMemcpyDeviceToHost,
-                             d->stream));
-      CU_TRY(cudaStreamSynchronize(d->stream));
-      if (time_kernels) {
-        flush_timing();
-        rep.check_s += now_s() - t_svc;
-      }
-      rep.d2h_bytes += sizeof(uint32_t) << d->log2PW;
-      uint32_t n_stop = 0;
-      for (uint32_t j = 0; j < B; ++j) { // stop rule, :395-403
-        const uint32_t s = virt[j];
-        const bool violated = (d->h_viol.p[s >> 5] >> (s & 31)) & 1u;
-        const uint32_t n_it = g - iter_start[in_gpu[j]];
-        stop[j] = (!violated || n_it >= prm->num_iter_max) ? 1 : 0;
-        if (stop[j]) {
-          ++n_stop;
-          if (iter_end[in_gpu[j]] == uint32_t(-1)) iter_end[in_gpu[j]] = g;
-        }
-      }
-      if (next_to_load == n_frames && n_stop == B) { // everything loaded and finished, :414-462
-        t_iter1 = now_s();
-        st = retire_frames(d, B, virt.data(), in_gpu.data(), results, results_on_device, &rep);
-        if (st != LDPC_B200_OK) return st;
-        rep.other_launches++;
+      if (sm.done) {
+        rep.global_iters = sm.g; // the loop index at which the reference breaks (:414-462)
         break;
       }
-      uint32_t n_new = std::min(n_frames - next_to_load, n_stop); // :464
-      if (simd_pairs) n_new &= ~1u;                               // ldpc_decoder_gpu.cpp:623
-      if (n_new > 0) {
-        // bring n_new finished frames to positions [0,n_new) of the slot order (:487-516)
-        uint32_t ctr = 0;
-        for (uint32_t i = 0; i < n_new; ++i) ctr += stop[i];
-        const uint32_t n_swaps = n_new - ctr;
-        uint32_t o = 0, q = n_new;
-        for (uint32_t i = 0; i < n_swaps; ++i) {
-          while (stop[o]) ++o;
-          while (!stop[q]) ++q;
-          std::swap(in_gpu[o], in_gpu[q]);
-          std::swap(virt[o], virt[q]);
-          ++o;
-          ++q;
-        }
-        for (uint32_t j = 0; j < n_new; ++j) {
-          tmp_slots[j] = virt[j];
-          tmp_frames[j] = in_gpu[j];
-        }
-        if (time_kernels) t_svc = now_s();
-        st = retire_frames(d, n_new, tmp_slots.data(), tmp_frames.data(), results, results_on_device, &rep);
-        if (st != LDPC_B200_OK) return st;
-        if (time_kernels) {
-          cudaStreamSynchronize(d->stream);
-          rep.retire_s += now_s() - t_svc;
-          t_svc = now_s();
-        }
-        st = stage_frames(d, in, next_to_load, n_new, tmp_slots.data(), &src_dev, &syn_dev, &rep);
-        if (st != LDPC_B200_OK) return st;
-        d->launch_refill(n_new, src_dev, syn_dev, prm->channel, prm->channel_param);
-        rep.other_launches += 3;
-        rep.frames_refilled += n_new;
-        if (time_kernels) {
-          cudaStreamSynchronize(d->stream);
-          rep.refill_s += now_s() - t_svc;
-        }
-        for (uint32_t j = 0; j < n_new; ++j) { // :604-609
-          in_gpu[j] = next_to_load + j;
-          iter_start[next_to_load + j] = g;
-        }
-        next_to_load += n_new;
-      }
     }
+    // frames the next refill may need: at most B beyond what has been loaded so far
+    st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, uint64_t(next_known) + B)));
+    if (st != LDPC_B200_OK) return st;
+    st = enqueue_service(period);
+    if (st != LDPC_B200_OK) return st;
+    enqueue_iterations(period + 1); // run ahead: no-ops once the scheduler has set `done`
     CU_TRY(cudaGetLastError());
-    ++g;
-    if (g > g_limit) return fail(LDPC_B200_ERR_INVALID, "scheduler made no progress (internal error)");
+    ++period;
+    if (period > period_limit) return fail(LDPC_B200_ERR_INVALID, "scheduler made no progress (internal error)");
   }
   CU_TRY(cudaEventRecord(ev_last, d->stream));
   CU_TRY(cudaStreamSynchronize(d->stream));
+  CU_TRY(cudaStreamSynchronize(d->copy_stream));
   float ms = 0;
   CU_TRY(cudaEventElapsedTime(&ms, ev_first, ev_last));
   rep.device_s = ms * 1e-3;
+  // the run-ahead period was enqueued but did no work
+  rep.cn_launches -= k_check;
+  rep.vn_launches -= k_check;
+  rep.other_launches -= 1;
+  rep.n_checks_run -= 1;
 
-  rep.max_iter = 0; // :616-628
+  // per-frame iteration counters live on the device (:616-628)
+  std::vector<uint32_t> it(2ull * n_frames);
+  CU_TRY(cudaMemcpy(it.data(), d->d_iter.p, sizeof(uint32_t) * 2ull * n_frames, cudaMemcpyDeviceToHost));
+  rep.max_iter = 0;
   rep.min_iter = uint32_t(-1);
   double avg = 0;
   for (uint32_t j = 0; j < n_frames; ++j) {
-    const uint32_t n = iter_end[j] - iter_start[j];
+    const uint32_t n = it[n_frames + j] - it[j];
     rep.max_iter = std::max(rep.max_iter, n);
     rep.min_iter = std::min(rep.min_iter, n);
     avg += n;
     if (iter_counts) iter_counts[j] = n;
   }
   rep.avg_iter = float(avg / n_frames);
-  rep.iter_time_per_vector = float((t_iter1 - t_iter0) / (double(g) * B));
-  rep.global_iters = g;
+  rep.iter_time_per_vector = rep.global_iters ? float(rep.device_s / (double(rep.global_iters) * B)) : 0.f;
   rep.elapsed_s = now_s() - t0;
   if (report) *report = rep;
   return LDPC_B200_OK;
@@ -770,6 +922,7 @@ ldpc_b200_status ldpc_b200_debug_refill(ldpc_b200_decoder *d, int32_t channel, f
   in.n_cols = cnt;
   std::vector<uint32_t> slots(cnt);
   for (uint32_t j = 0; j < cnt; ++j) slots[j] = j;
+  CU_TRY(cudaMemsetAsync(d->d_state.p, 0, sizeof(dev::SchedState), d->stream)); // a finished decode leaves done = 1
   const void *src_dev = nullptr;
   const uint32_t *syn_dev = nullptr;
   ldpc_b200_status st = stage_frames(d, in, 0, cnt, slots.data(), &src_dev, &syn_dev, nullptr);

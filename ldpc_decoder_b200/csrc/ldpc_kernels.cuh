@@ -189,7 +189,9 @@ template <class Tr> __device__ __forceinline__ uint32_t load_frame_bits(const ui
 template <class Tr>
 __global__ void __launch_bounds__(kThreads)
     cn_update_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
-                     const uint16_t *__restrict__ phi_table, uint32_t n_checks, uint32_t log2_g) {
+                     const uint16_t *__restrict__ phi_table, uint32_t n_checks, uint32_t log2_g,
+                     const uint32_t *__restrict__ done) {
+  if (done && *done) return; // the device-side scheduler has retired every frame: run-ahead launches are no-ops
   const uint16_t *tab = stage_phi_table<Tr>(phi_table);
   const uint32_t G = 1u << log2_g;
   const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
@@ -266,7 +268,9 @@ template <class Tr, bool kFinalBits>
 __global__ void __launch_bounds__(kThreads)
     vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ col_ptr,
                      const uint32_t *__restrict__ in_to_out, uint8_t *__restrict__ hard,
-                     const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t log2_g) {
+                     const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t log2_g,
+                     const uint32_t *__restrict__ done) {
+  if (done && *done) return;
   const uint16_t *tab = stage_phi_table<Tr>(phi_table);
   const uint32_t G = 1u << log2_g;
   const size_t hard_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
@@ -346,7 +350,9 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     syndrome_check_kernel(const uint32_t *__restrict__ syn, const uint32_t *__restrict__ hard,
                           const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ edge_var,
-                          uint32_t *__restrict__ viol, uint32_t n_checks, uint32_t log2_pw) {
+                          uint32_t *__restrict__ viol, uint32_t n_checks, uint32_t log2_pw,
+                          const uint32_t *__restrict__ done) {
+  if (done && *done) return;
   const uint32_t PW = 1u << log2_pw;
   const uint64_t total = uint64_t(n_checks) << log2_pw;
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x; // multiple of PW: a thread keeps its word w
@@ -377,9 +383,12 @@ struct RefillEntry {     // one new frame
 template <class Tr, typename Elem>
 __global__ void __launch_bounds__(kThreads)
     refill_kernel(Elem *__restrict__ msg, Elem *__restrict__ llr0, const Elem *__restrict__ src,
-                  const RefillEntry *__restrict__ entries, uint32_t n_new, const uint32_t *__restrict__ col_ptr,
+                  const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
+                  const uint32_t *__restrict__ col_ptr,
                   const uint32_t *__restrict__ in_to_out, const uint16_t *__restrict__ phi_table, uint32_t n_vars,
                   uint32_t n_regular, uint32_t log2_p, int channel, float param) {
+  const uint32_t n_new = *n_new_ptr; // written by the scheduler kernel (or the host for kernel-level calls)
+  if (n_new == 0) return;
   const uint64_t total = uint64_t(n_vars) * n_new;
   for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
        item += uint64_t(gridDim.x) * blockDim.x) {
@@ -411,8 +420,10 @@ __global__ void __launch_bounds__(kThreads)
 // One thread = (check c, slot word w) for words that received new frames: replace those slots' target bits.
 __global__ void __launch_bounds__(kThreads)
     refill_syndrome_kernel(uint32_t *__restrict__ syn, const uint32_t *__restrict__ src_syn,
-                           const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ new_mask,
-                           const uint32_t *__restrict__ slot_entry, uint32_t n_checks, uint32_t log2_pw) {
+                           const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
+                           const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
+                           uint32_t n_checks, uint32_t log2_pw) {
+  if (*n_new_ptr == 0) return;
   const uint32_t PW = 1u << log2_pw;
   const uint64_t total = uint64_t(n_checks) << log2_pw;
   for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
@@ -475,6 +486,210 @@ __global__ void __launch_bounds__(128)
       ++k;
     }
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- device-side scheduler
+// The reference decides on the HOST, after a blocking read of P flag bytes, which frames stop, which are
+// retired and where the new ones go (ldpc_decoder_gpu.cu:374-413, 464-516, 604-609).  Here one CTA does it on
+// the device right after the syndrome check, so the next flood iterations never wait for the host:
+//   stop rule -> n_new -> the reference's swap pairing (as a prefix-sum compaction of finished positions)
+//   -> extraction list, refill list, slot masks, per-frame iteration counters, a summary for the host.
+struct SchedConst {
+  uint32_t n_frames, batch, log2_p, k_check, imax, simd_pairs, syn_words, res_words;
+  uint32_t input_mode;   // 0 interleaved [i][n_cols], 1 frame-major, 2 ring of interleaved blocks, 3 frame-major ring
+  uint32_t n_cols;       // frames physically present in the input (pool or n_frames)
+  uint32_t ring_frames, ring_block, n_regular;
+  uint32_t syn_ring;     // syndromes staged in a ring (position f % ring_frames) instead of read in place
+  uint32_t results_ring; // results go to a [P][W] device ring (host drains it) instead of results[frame]
+  uint32_t pad;
+  uint64_t frame_stride;
+};
+struct SchedState {
+  uint32_t next_to_load, g, done, period;
+};
+struct SchedSummary {
+  uint32_t n_new, n_retired, next_to_load, done, g, n_stop, period, pad;
+};
+
+__device__ __forceinline__ void make_refill_entry(const SchedConst &c, uint32_t frame, uint32_t slot, RefillEntry &en) {
+  const uint32_t col = frame % c.n_cols;
+  if (c.input_mode == 0) {
+    en.src_offset = col;
+    en.src_stride = c.n_cols;
+  } else if (c.input_mode == 1) {
+    en.src_offset = uint64_t(col) * c.frame_stride;
+    en.src_stride = 1;
+  } else if (c.input_mode == 2) {
+    const uint32_t r = frame % c.ring_frames;
+    en.src_offset = uint64_t(r / c.ring_block) * c.n_regular * c.ring_block + (r % c.ring_block);
+    en.src_stride = c.ring_block;
+  } else {
+    en.src_offset = uint64_t(frame % c.ring_frames) * c.n_regular;
+    en.src_stride = 1;
+  }
+  en.syn_offset = uint64_t(c.syn_ring ? frame % c.ring_frames : col) * c.syn_words;
+  en.slot = slot;
+  en.pad = 0;
+}
+
+constexpr int kSchedThreads = 1024;
+constexpr int kMaxSlots = 8192;
+
+// block-wide exclusive scan of one value per thread (1024 threads)
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_warp, uint32_t &total) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+      if (lane >= d) w += y;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  total = s_warp[31];
+  const uint32_t base = warp ? s_warp[warp - 1] : 0u;
+  __syncthreads();
+  return base + x - v;
+}
+
+// First batch: frames 0..batch-1 into slots 0..batch-1 (ldpc_decoder_gpu.cu:300-315).
+__global__ void __launch_bounds__(kSchedThreads)
+    sched_init_kernel(SchedConst c, SchedState *st, uint32_t *in_gpu, uint32_t *virt, uint32_t *iter_start,
+                      uint32_t *iter_end, RefillEntry *entries, uint32_t *n_new_out, uint32_t *new_mask,
+                      uint32_t *retire_mask, uint32_t *slot_entry) {
+  const uint32_t PW = (1u << c.log2_p) >> 5;
+  for (uint32_t i = threadIdx.x; i < c.n_frames; i += blockDim.x) iter_start[i] = iter_end[i] = 0xFFFFFFFFu;
+  for (uint32_t w = threadIdx.x; w < PW; w += blockDim.x) {
+    const uint32_t lo = w * 32u;
+    new_mask[w] = c.batch >= lo + 32u ? 0xFFFFFFFFu : (c.batch > lo ? (1u << (c.batch - lo)) - 1u : 0u);
+    retire_mask[w] = 0;
+  }
+  for (uint32_t j = threadIdx.x; j < c.batch; j += blockDim.x) {
+    in_gpu[j] = virt[j] = j;
+    slot_entry[j] = j;
+    make_refill_entry(c, j, j, entries[j]);
+  }
+  if (threadIdx.x == 0) {
+    st->next_to_load = c.batch;
+    st->g = c.k_check; // the first check happens at global iteration k (after k+1 flood iterations)
+    st->done = 0;
+    st->period = 0;
+    *n_new_out = c.batch;
+  }
+}
+
+__global__ void __launch_bounds__(kSchedThreads)
+    sched_kernel(SchedConst c, SchedState *st, const uint32_t *__restrict__ viol, uint32_t *in_gpu, uint32_t *virt,
+                 uint32_t *iter_start, uint32_t *iter_end, RefillEntry *entries, ExtractEntry *slot_dst,
+                 uint32_t *n_new_out, uint32_t *new_mask, uint32_t *retire_mask, uint32_t *slot_entry,
+                 uint32_t *retired_frames, SchedSummary *summary) {
+  __shared__ uint8_t s_stop[kMaxSlots];
+  __shared__ uint32_t s_partner[kMaxSlots]; // finished positions >= n_new, compacted in position order
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_n_new, s_all_done;
+  const uint32_t B = c.batch, PW = (1u << c.log2_p) >> 5, tid = threadIdx.x;
+  if (st->done) { // run-ahead period after the end: nothing to retire or load
+    for (uint32_t w = tid; w < PW; w += blockDim.x) new_mask[w] = retire_mask[w] = 0;
+    if (tid == 0) {
+      *n_new_out = 0;
+      SchedSummary sm = {0, 0, st->next_to_load, 1, st->g, 0, st->period, 0};
+      *summary = sm;
+      st->period++;
+    }
+    return;
+  }
+  const uint32_t g = st->g, next = st->next_to_load, period = st->period;
+  // stop rule (ldpc_decoder_gpu.cu:395-403)
+  const uint32_t chunk = (B + blockDim.x - 1) / blockDim.x;
+  const uint32_t j0 = min(B, tid * chunk), j1 = min(B, j0 + chunk);
+  uint32_t my_stop = 0;
+  for (uint32_t j = j0; j < j1; ++j) {
+    const uint32_t s = virt[j], f = in_gpu[j];
+    const bool violated = (viol[s >> 5] >> (s & 31u)) & 1u;
+    const uint32_t n_it = g - iter_start[f];
+    const bool stop = !violated || n_it >= c.imax;
+    s_stop[j] = stop;
+    if (stop) {
+      ++my_stop;
+      if (iter_end[f] == 0xFFFFFFFFu) iter_end[f] = g;
+    }
+  }
+  uint32_t n_stop;
+  block_exclusive_scan(my_stop, s_warp, n_stop);
+  if (tid == 0) {
+    const uint32_t remaining = c.n_frames - next;
+    s_all_done = (remaining == 0 && n_stop == B); // :414
+    uint32_t n_new = min(remaining, n_stop);      // :464
+    if (c.simd_pairs) n_new &= ~1u;               // ldpc_decoder_gpu.cpp:623
+    s_n_new = s_all_done ? 0u : n_new;
+  }
+  for (uint32_t w = tid; w < PW; w += blockDim.x) new_mask[w] = retire_mask[w] = 0;
+  __syncthreads();
+  const uint32_t n_new = s_n_new;
+  const bool all_done = s_all_done;
+  if (all_done) { // retire everything, in position order (:437-460)
+    for (uint32_t j = j0; j < j1; ++j) {
+      const uint32_t s = virt[j], f = in_gpu[j];
+      atomicOr(retire_mask + (s >> 5), 1u << (s & 31u));
+      slot_dst[s].dst_offset = c.results_ring ? uint64_t(j) * c.res_words : uint64_t(f) * c.res_words;
+      retired_frames[j] = f;
+    }
+  } else if (n_new > 0) {
+    // the reference pairs, in position order, every still-running position o < n_new with a finished position
+    // q >= n_new and swaps them (:487-516): rank both sets with a scan, match equal ranks
+    uint32_t my_a = 0, my_b = 0;
+    for (uint32_t j = j0; j < j1; ++j) {
+      if (j < n_new) my_a += !s_stop[j];
+      else my_b += s_stop[j];
+    }
+    uint32_t tot_a, tot_b;
+    uint32_t rank_a = block_exclusive_scan(my_a, s_warp, tot_a);
+    uint32_t rank_b = block_exclusive_scan(my_b, s_warp, tot_b);
+    for (uint32_t j = j0; j < j1; ++j)
+      if (j >= n_new && s_stop[j]) s_partner[rank_b++] = j;
+    __syncthreads();
+    for (uint32_t j = j0; j < j1; ++j)
+      if (j < n_new && !s_stop[j]) {
+        const uint32_t q = s_partner[rank_a++];
+        const uint32_t f = in_gpu[j], s = virt[j];
+        in_gpu[j] = in_gpu[q];
+        virt[j] = virt[q];
+        in_gpu[q] = f;
+        virt[q] = s;
+      }
+    __syncthreads();
+    // positions [0,n_new) now hold finished frames: retire them and load frames next.. into their slots
+    for (uint32_t j = tid; j < n_new; j += blockDim.x) {
+      const uint32_t s = virt[j], f_old = in_gpu[j], f_new = next + j;
+      atomicOr(retire_mask + (s >> 5), 1u << (s & 31u));
+      atomicOr(new_mask + (s >> 5), 1u << (s & 31u));
+      slot_dst[s].dst_offset = c.results_ring ? uint64_t(j) * c.res_words : uint64_t(f_old) * c.res_words;
+      retired_frames[j] = f_old;
+      slot_entry[s] = j;
+      make_refill_entry(c, f_new, s, entries[j]);
+      in_gpu[j] = f_new; // :604-609
+      iter_start[f_new] = g;
+    }
+  }
+  if (tid == 0) {
+    *n_new_out = n_new;
+    st->next_to_load = next + n_new;
+    st->g = g + c.k_check;
+    st->done = all_done ? 1u : 0u;
+    st->period = period + 1;
+    SchedSummary sm = {n_new, all_done ? B : n_new, next + n_new, all_done ? 1u : 0u, g, n_stop, period, 0};
+    *summary = sm;
   }
 }
 
