@@ -692,12 +692,12 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
         while (f < f1) {
           const uint32_t r = f % ring_frames;
           const uint32_t blk0 = r / ring_block;
-          const uint32_t run = std::min(f1 - f, ring_frames - blk0 * ring_block); // up to the end of the ring
+          const uint32_t run = std::min(f1 - f, ring_frames - r); // up to the end of the ring
           const uint32_t n_blk = (r % ring_block + run + ring_block - 1) / ring_block;
           const size_t off = size_t(blk0) * n_reg * ring_block * es, bytes = size_t(n_blk) * n_reg * ring_block * es;
           CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
           rep.h2d_bytes += bytes;
-          f += std::min(run, n_blk * ring_block - r % ring_block);
+          f += run;
         }
       } else {
         parallel_for(f1 - f0, d->host_threads, [&](size_t a, size_t b2) {
