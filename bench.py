@@ -287,13 +287,23 @@ def main():
     vn_gbs = vn_bytes * n_vn / vn_s / 1e9
     pair_gbs = (cn_bytes * n_cn + vn_bytes * n_vn) / (cn_s + vn_s) / 1e9
     dev_s = sum(r["device_s"] for r in reps)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.precision}:{P}")
+        if tr and args.log2_n == 20:
+            traffic = {"cn": tr["cn"], "vn": tr["vn"], "pair": tr["cn"] + tr["vn"], "algorithmic_pair": cn_bytes + vn_bytes,
+                       "source": tr["source"]}
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": "cn_update_kernel + vn_update_kernel (one flood iteration)",
         "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak, "peak_source": peak_kind,
-        "traffic": None,
+        "traffic": traffic,
         "cn": {"gbs": cn_gbs, "frac": cn_gbs / peak, "avg_ms": 1e3 * cn_s / n_cn, "bytes_per_launch": cn_bytes},
         "vn": {"gbs": vn_gbs, "frac": vn_gbs / peak, "avg_ms": 1e3 * vn_s / n_vn, "bytes_per_launch": vn_bytes},
         "kernel_share_of_step": (cn_s + vn_s) / dev_s if dev_s else None,
+        "timed": {"cn_s": cn_s, "vn_s": vn_s, "device_s": dev_s, "n_cn": int(n_cn), "n_vn": int(n_vn),
+                  "global_iters": [int(r["global_iters"]) for r in reps]},
         "service_s_per_step": {k: sum(r[k] for r in reps) / len(reps) for k in ("check_s", "retire_s", "refill_s")},
         "frames_refilled_per_step": sum(r["frames_refilled"] for r in reps) / len(reps),
     }

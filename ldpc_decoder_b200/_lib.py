@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldpc_b200.so")
+LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(_HERE, "libldpc_b200.so")  # override: A/B kernel experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CODE, ERR_MULTIPLE_32, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_ALIST = range(8)

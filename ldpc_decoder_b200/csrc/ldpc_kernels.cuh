@@ -84,6 +84,9 @@ struct TraitsF32 {
   static constexpr int kFramesPerVec = 4;
   static constexpr uint32_t kSignMask = 0x80000000u;
   static constexpr bool kUsesTable = false;
+  // software prefetch of the next item's indices: measured on B200 (scripts/kernel_perf.py), it only pays in the
+  // fp16 variable-node pass (+3-4 %); elsewhere the extra registers cost a resident CTA
+  static constexpr bool kPrefetchCN = false, kPrefetchVN = false;
   __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFFFFFFu; }
   __device__ static __forceinline__ uint32_t add_w(uint32_t a, uint32_t b) {
     return __float_as_uint(__uint_as_float(a) + __uint_as_float(b));
@@ -113,6 +116,7 @@ struct TraitsF16 {
   static constexpr int kFramesPerVec = 8;
   static constexpr uint32_t kSignMask = 0x80008000u;
   static constexpr bool kUsesTable = true;
+  static constexpr bool kPrefetchCN = false, kPrefetchVN = true;
   __device__ static __forceinline__ __half2 h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
   __device__ static __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
   __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFF7FFFu; }
@@ -186,6 +190,8 @@ template <class Tr> __device__ __forceinline__ uint32_t load_frame_bits(const ui
 // ---------------------------------------------------------------- check-node pass
 // One thread = (check c, frame vector g).  S = sum |m_e|; every edge gets phi_abs(S - |m_e|) with
 // sign = sign(m_e) xor parity, parity = syndrome bit xor (number of non-negative inputs) (flood.cu:77-115).
+// The row offsets and syndrome bits of the thread's NEXT item are fetched while the current row's messages are
+// in flight, so the dependent index -> message load chain is off the critical path.
 template <class Tr>
 __global__ void __launch_bounds__(kThreads)
     cn_update_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
@@ -196,14 +202,25 @@ __global__ void __launch_bounds__(kThreads)
   const uint32_t G = 1u << log2_g;
   const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
   const uint64_t total = uint64_t(n_checks) << log2_g;
-  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
-       item += uint64_t(gridDim.x) * blockDim.x) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t a_next = 0, b_next = 0, sbits_next = 0;
+  if (Tr::kPrefetchCN && item < total) {
     const uint32_t c = uint32_t(item >> log2_g);
+    a_next = __ldg(row_ptr + c);
+    b_next = __ldg(row_ptr + c + 1);
+    sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, uint32_t(item) & (G - 1u));
+  }
+  for (; item < total; item += stride) {
     const uint32_t g = uint32_t(item) & (G - 1u);
-    const uint32_t a = __ldg(row_ptr + c), b = __ldg(row_ptr + c + 1);
-    const uint32_t deg = b - a;
+    if (!Tr::kPrefetchCN) {
+      const uint32_t c = uint32_t(item >> log2_g);
+      a_next = __ldg(row_ptr + c);
+      b_next = __ldg(row_ptr + c + 1);
+      sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
+    }
+    const uint32_t a = a_next, deg = b_next - a_next, sbits = sbits_next;
     uint4 *p = msg + (size_t(a) << log2_g) + g;
-    const uint32_t sbits = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
     // parity seed: syndrome bit xor (deg & 1); xor-ing the raw sign bits of all inputs then gives
     // syndrome ^ #(non-negative inputs)
     const uint32_t odd = (deg & 1u) ? Tr::kSignMask : 0u;
@@ -216,6 +233,12 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
       for (int k = 0; k < kMaxRegDeg; ++k)
         if (k < deg) m[k] = ld_stream(p + (size_t(k) << log2_g));
+      if (Tr::kPrefetchCN && item + stride < total) { // next item's indices behind the message loads
+        const uint32_t c = uint32_t((item + stride) >> log2_g);
+        a_next = __ldg(row_ptr + c);
+        b_next = __ldg(row_ptr + c + 1);
+        sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
+      }
 #pragma unroll
       for (int k = 0; k < kMaxRegDeg; ++k)
         if (k < deg) {
@@ -238,6 +261,12 @@ __global__ void __launch_bounds__(kThreads)
           st_stream(p + (size_t(k) << log2_g), o);
         }
     } else {
+      if (Tr::kPrefetchCN && item + stride < total) {
+        const uint32_t c = uint32_t((item + stride) >> log2_g);
+        a_next = __ldg(row_ptr + c);
+        b_next = __ldg(row_ptr + c + 1);
+        sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
+      }
       for (uint32_t k = 0; k < deg; ++k) {
         uint4 mk = ld_cached(p + (size_t(k) << log2_g));
 #pragma unroll
@@ -264,6 +293,7 @@ __global__ void __launch_bounds__(kThreads)
 // ---------------------------------------------------------------- variable-node pass
 // One thread = (variable v, frame vector g).  T = llr0 + sum of incoming c2v in CSC order; every edge gets
 // phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).
+// The gather list of the thread's NEXT item is fetched while the current messages are in flight.
 template <class Tr, bool kFinalBits>
 __global__ void __launch_bounds__(kThreads)
     vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ col_ptr,
@@ -275,22 +305,46 @@ __global__ void __launch_bounds__(kThreads)
   const uint32_t G = 1u << log2_g;
   const size_t hard_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
   const uint64_t total = uint64_t(n_vars) << log2_g;
-  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
-       item += uint64_t(gridDim.x) * blockDim.x) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t a_next = 0, deg_next = 0;
+  uint32_t rows_next[kMaxRegDeg];
+  if (Tr::kPrefetchVN && item < total) {
+    const uint32_t v = uint32_t(item >> log2_g);
+    a_next = __ldg(col_ptr + v);
+    deg_next = __ldg(col_ptr + v + 1) - a_next;
+#pragma unroll
+    for (int k = 0; k < kMaxRegDeg; ++k)
+      if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
+  }
+  for (; item < total; item += stride) {
     const uint32_t v = uint32_t(item >> log2_g);
     const uint32_t g = uint32_t(item) & (G - 1u);
-    const uint32_t a = __ldg(col_ptr + v), b = __ldg(col_ptr + v + 1);
-    const uint32_t deg = b - a;
+    if (!Tr::kPrefetchVN) {
+      a_next = __ldg(col_ptr + v);
+      deg_next = __ldg(col_ptr + v + 1) - a_next;
+#pragma unroll
+      for (int k = 0; k < kMaxRegDeg; ++k)
+        if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
+    }
+    const uint32_t a = a_next, deg = deg_next;
     uint4 T = ld_stream(llr0 + (size_t(v) << log2_g) + g);
     if (deg <= kMaxRegDeg) {
       uint4 m[kMaxRegDeg];
-      uint4 *p[kMaxRegDeg];
+      uint32_t rows[kMaxRegDeg];
 #pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg) {
-          p[k] = msg + (size_t(__ldg(in_to_out + a + k)) << log2_g) + g;
-          m[k] = ld_stream(p[k]);
-        }
+      for (int k = 0; k < kMaxRegDeg; ++k) {
+        rows[k] = rows_next[k];
+        if (k < deg) m[k] = ld_stream(msg + (size_t(rows[k]) << log2_g) + g);
+      }
+      if (Tr::kPrefetchVN && item + stride < total) { // next item's gather list behind the message loads
+        const uint32_t vn = uint32_t((item + stride) >> log2_g);
+        a_next = __ldg(col_ptr + vn);
+        deg_next = __ldg(col_ptr + vn + 1) - a_next;
+#pragma unroll
+        for (int k = 0; k < kMaxRegDeg; ++k)
+          if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
+      }
 #pragma unroll
       for (int k = 0; k < kMaxRegDeg; ++k)
         if (k < deg) {
@@ -307,9 +361,17 @@ __global__ void __launch_bounds__(kThreads)
             const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab);
             word(o, w) = (r & ~Tr::kSignMask) | (pre & Tr::kSignMask);
           }
-          st_stream(p[k], o);
+          st_stream(msg + (size_t(rows[k]) << log2_g) + g, o);
         }
     } else {
+      if (Tr::kPrefetchVN && item + stride < total) {
+        const uint32_t vn = uint32_t((item + stride) >> log2_g);
+        a_next = __ldg(col_ptr + vn);
+        deg_next = __ldg(col_ptr + vn + 1) - a_next;
+#pragma unroll
+        for (int k = 0; k < kMaxRegDeg; ++k)
+          if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
+      }
       for (uint32_t k = 0; k < deg; ++k) {
         const uint4 mk = ld_cached(msg + (size_t(__ldg(in_to_out + a + k)) << log2_g) + g);
 #pragma unroll

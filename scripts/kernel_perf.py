@@ -1,0 +1,29 @@
+"""Quick per-pass bandwidth of the CN / VN kernels through the kernel-level C-ABI entry points."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import ldpc_decoder_b200 as L
+from ldpc_decoder_b200 import alist, harness
+
+configs = sys.argv[1:] or ["fp16:10", "fp16:12", "fp32:10"]
+gen = alist.make_readme_shaped_code(20, seed=1)
+code = L.Code.from_generated(gen)
+E, N, M = gen.n_edges, gen.n_vars, gen.n_checks
+for cfg in configs:
+    prec, log2p = cfg.split(":")
+    log2p = int(log2p)
+    P = 1 << log2p
+    dt = np.float16 if prec == "fp16" else np.float32
+    s = 2 if prec == "fp16" else 4
+    dec = L.Decoder(code, L.FP16 if prec == "fp16" else L.FP32, log2p)
+    inp, syn, bits = harness.make_frames(gen, 32, "awgn", 0.83, seed=1, dtype=dt)
+    n_reg = N - gen.n_erased
+    reps = P // 32
+    dec.refill(L.AWGN, harness.channel_param("awgn", 0.83), np.tile(inp[:n_reg], (1, reps)), np.tile(syn, (reps, 1)))
+    dec.iterate(3)
+    cn_ms, vn_ms = dec.iterate(20, timed=True)
+    cn_b = (2 * E * s + 4 * ((M + 31) // 32)) * P
+    vn_b = (2 * E + N) * s * P
+    print(f"{cfg}: CN {cn_ms/20:.3f} ms {cn_b/(cn_ms/20*1e-3)/1e9:.0f} GB/s | VN {vn_ms/20:.3f} ms {vn_b/(vn_ms/20*1e-3)/1e9:.0f} GB/s | "
+          f"pair {(cn_b+vn_b)/((cn_ms+vn_ms)/20*1e-3)/1e9:.0f} GB/s = {(cn_b+vn_b)/((cn_ms+vn_ms)/20*1e-3)/1e9/6551.4:.3f} of peak", flush=True)
+    del dec
