@@ -256,15 +256,15 @@ struct ldpc_b200_decoder {
   // refill kernels: entries, count, masks are already in device memory (scheduler kernel or host upload)
   void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param) {
     const uint32_t n_regular = N - n_erased;
+    uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p), *l0 = reinterpret_cast<uint4 *>(d_llr0.p);
     if (precision == LDPC_B200_FP32)
-      dev::refill_kernel<dev::TraitsF32, float><<<grid_misc, dev::kThreads, 0, stream>>>(
-          reinterpret_cast<float *>(d_msg.p), reinterpret_cast<float *>(d_llr0.p), static_cast<const float *>(src),
-          d_refill.p, d_n_new.p, d_col_ptr.p, d_in_to_out.p, nullptr, N, n_regular, log2P, channel, param);
+      dev::refill_kernel<dev::TraitsF32><<<grid_misc, dev::kThreads, 0, stream>>>(
+          msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p, d_col_ptr.p, d_in_to_out.p, nullptr, N,
+          n_regular, log2G, channel, param);
     else
-      dev::refill_kernel<dev::TraitsF16, uint16_t><<<grid_misc, dev::kThreads, 0, stream>>>(
-          reinterpret_cast<uint16_t *>(d_msg.p), reinterpret_cast<uint16_t *>(d_llr0.p),
-          static_cast<const uint16_t *>(src), d_refill.p, d_n_new.p, d_col_ptr.p, d_in_to_out.p, d_phi_table.p, N,
-          n_regular, log2P, channel, param);
+      dev::refill_kernel<dev::TraitsF16><<<grid_misc, dev::kThreads, 0, stream>>>(
+          msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p, d_col_ptr.p, d_in_to_out.p,
+          d_phi_table.p, N, n_regular, log2G, channel, param);
     dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
                                                                          d_new_mask.p, d_slot_entry.p, M, log2PW);
   }

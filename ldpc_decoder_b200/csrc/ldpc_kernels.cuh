@@ -440,42 +440,72 @@ struct RefillEntry {     // one new frame
   uint32_t pad;
 };
 
-// One thread = (variable i, new frame t), t fastest: prior = llr(channel value) (0 for punctured variables),
-// and phi(prior) goes to every edge of the variable (flood.cu:47-75, 297-323).
-template <class Tr, typename Elem>
+// One thread = (variable i, 16-byte slot vector g).  New frames land in scattered slots, so a 2- or 4-byte store
+// per (row, slot) would cost a 32-byte sector read-modify-write each.  Instead every vector that contains at least
+// one new slot is rewritten whole: read 16 B, replace the new lanes, write 16 B -- for the prior row and for
+// every edge row of the variable.  prior = llr(channel value) (0 for punctured variables), edges get phi(prior)
+// (flood.cu:47-75, 297-323).  Vectors without new slots are skipped; a vector of only new slots is not read.
+template <class Tr>
 __global__ void __launch_bounds__(kThreads)
-    refill_kernel(Elem *__restrict__ msg, Elem *__restrict__ llr0, const Elem *__restrict__ src,
+    refill_kernel(uint4 *__restrict__ msg, uint4 *__restrict__ llr0, const void *__restrict__ src,
                   const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
-                  const uint32_t *__restrict__ col_ptr,
-                  const uint32_t *__restrict__ in_to_out, const uint16_t *__restrict__ phi_table, uint32_t n_vars,
-                  uint32_t n_regular, uint32_t log2_p, int channel, float param) {
-  const uint32_t n_new = *n_new_ptr; // written by the scheduler kernel (or the host for kernel-level calls)
-  if (n_new == 0) return;
-  const uint64_t total = uint64_t(n_vars) * n_new;
+                  const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
+                  const uint32_t *__restrict__ col_ptr, const uint32_t *__restrict__ in_to_out,
+                  const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t n_regular, uint32_t log2_g,
+                  int channel, float param) {
+  if (*n_new_ptr == 0) return; // written by the scheduler kernel (or the host for kernel-level calls)
+  constexpr int V = Tr::kFramesPerVec;
+  constexpr uint32_t kFull = (1u << V) - 1u;
+  const uint32_t G = 1u << log2_g;
+  const uint64_t total = uint64_t(n_vars) << log2_g;
   for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
        item += uint64_t(gridDim.x) * blockDim.x) {
-    const uint32_t i = uint32_t(item / n_new);
-    const uint32_t t = uint32_t(item - uint64_t(i) * n_new);
-    const RefillEntry en = entries[t];
-    Elem llr, out;
-    if (sizeof(Elem) == 4) {
-      uint32_t raw = 0;
-      if (i < n_regular) raw = TraitsF32::to_llr(reinterpret_cast<const uint32_t *>(src)[en.src_offset + uint64_t(i) * en.src_stride], channel, param);
-      const uint32_t r = __float_as_uint(phi_abs_f32(__uint_as_float(raw & 0x7FFFFFFFu)));
-      const uint32_t o = (r & 0x7FFFFFFFu) | (raw & 0x80000000u);
-      llr = *reinterpret_cast<const Elem *>(&raw);
-      out = *reinterpret_cast<const Elem *>(&o);
-    } else {
-      uint16_t raw = 0;
-      if (i < n_regular) raw = TraitsF16::to_llr(reinterpret_cast<const uint16_t *>(src)[en.src_offset + uint64_t(i) * en.src_stride], channel, param);
-      const uint16_t r = __ldg(phi_table + (raw & 0x7FFFu));
-      const uint16_t o = uint16_t((r & 0x7FFFu) | (raw & 0x8000u));
-      llr = *reinterpret_cast<const Elem *>(&raw);
-      out = *reinterpret_cast<const Elem *>(&o);
+    const uint32_t i = uint32_t(item >> log2_g);
+    const uint32_t g = uint32_t(item) & (G - 1u);
+    const uint32_t nm = load_frame_bits<Tr>(reinterpret_cast<const uint8_t *>(new_mask), g);
+    if (nm == 0) continue;
+    uint4 L = make_uint4(0, 0, 0, 0), O = make_uint4(0, 0, 0, 0), SEL = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if ((nm >> j) & 1u) {
+        const RefillEntry en = entries[__ldg(slot_entry + g * V + j)];
+        const uint64_t at = en.src_offset + uint64_t(i) * en.src_stride;
+        if (V == 4) {
+          uint32_t raw = 0;
+          if (i < n_regular) raw = TraitsF32::to_llr(__ldg(static_cast<const uint32_t *>(src) + at), channel, param);
+          const uint32_t r = __float_as_uint(phi_abs_f32(__uint_as_float(raw & 0x7FFFFFFFu)));
+          word(L, j & 3) = raw;
+          word(O, j & 3) = (r & 0x7FFFFFFFu) | (raw & 0x80000000u);
+          word(SEL, j & 3) = 0xFFFFFFFFu;
+        } else {
+          uint32_t raw = 0;
+          if (i < n_regular) raw = TraitsF16::to_llr(__ldg(static_cast<const uint16_t *>(src) + at), channel, param);
+          const uint32_t r = __ldg(phi_table + (raw & 0x7FFFu));
+          const uint32_t o = (r & 0x7FFFu) | (raw & 0x8000u);
+          const int sh = (j & 1) * 16;
+          word(L, (j >> 1) & 3) |= raw << sh;
+          word(O, (j >> 1) & 3) |= o << sh;
+          word(SEL, (j >> 1) & 3) |= 0xFFFFu << sh;
+        }
+      }
     }
-    llr0[(size_t(i) << log2_p) + en.slot] = llr;
+    {
+      uint4 *p = llr0 + (size_t(i) << log2_g) + g;
+      uint4 old = make_uint4(0, 0, 0, 0);
+      if (nm != kFull) old = ld_stream(p);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(L, w);
+      st_stream(p, old);
+    }
     const uint32_t a = __ldg(col_ptr + i), b = __ldg(col_ptr + i + 1);
-    for (uint32_t ie = a; ie < b; ++ie) msg[(size_t(__ldg(in_to_out + ie)) << log2_p) + en.slot] = out;
+    for (uint32_t ie = a; ie < b; ++ie) {
+      uint4 *p = msg + (size_t(__ldg(in_to_out + ie)) << log2_g) + g;
+      uint4 old = make_uint4(0, 0, 0, 0);
+      if (nm != kFull) old = ld_stream(p);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(O, w);
+      st_stream(p, old);
+    }
   }
 }
 
