@@ -208,6 +208,7 @@ struct ldpc_b200_decoder {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   int grid_cn = 1, grid_vn = 1, grid_vnb = 1, grid_misc = 1;
   size_t smem_tab = 0;
+  uint32_t tab_last = dev::kPhiTableSize - 1; // first index from which the fp16 phi table is all zero
 
   ~ldpc_b200_decoder() {
     for (cudaEvent_t e : {ev_a, ev_b, ev_staged, ev_refilled, ev_period[0], ev_period[1], ev_extracted[0], ev_extracted[1]})
@@ -218,35 +219,23 @@ struct ldpc_b200_decoder {
   const uint32_t *done_flag() const { return &d_state.p->done; }
 
   // ---- launches -----------------------------------------------------------
+  // kernel instantiations are chosen once per decoder (precision, register-resident degree D)
+  typedef void (*cn_fn)(uint4 *, const uint32_t *, const uint8_t *, const uint16_t *, uint32_t, uint32_t, uint32_t,
+                        const uint32_t *);
+  typedef void (*vn_fn)(uint4 *, const uint4 *, const uint32_t *, const uint32_t *, uint8_t *, const uint16_t *,
+                        uint32_t, uint32_t, uint32_t, const uint32_t *);
+  cn_fn k_cn = nullptr;
+  vn_fn k_vn = nullptr, k_vnb = nullptr;
+  int deg_cn = 8, deg_vn = 8;
   void launch_cn() {
-    if (precision == LDPC_B200_FP32)
-      dev::cn_update_kernel<dev::TraitsF32><<<grid_cn, dev::kThreads, 0, stream>>>(
-          reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), nullptr, M, log2G,
-          done_flag());
-    else
-      dev::cn_update_kernel<dev::TraitsF16><<<grid_cn, dev::kThreads, smem_tab, stream>>>(
-          reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p, M,
-          log2G, done_flag());
+    k_cn<<<grid_cn, dev::kThreads, smem_tab, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
+                                                      reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
+                                                      tab_last, M, log2G, done_flag());
   }
   void launch_vn(bool bits) {
-    uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p);
-    const uint4 *l0 = reinterpret_cast<const uint4 *>(d_llr0.p);
-    uint8_t *hard = reinterpret_cast<uint8_t *>(d_hard.p);
-    if (precision == LDPC_B200_FP32) {
-      if (bits)
-        dev::vn_update_kernel<dev::TraitsF32, true><<<grid_vnb, dev::kThreads, 0, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G, done_flag());
-      else
-        dev::vn_update_kernel<dev::TraitsF32, false><<<grid_vn, dev::kThreads, 0, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, nullptr, N, log2G, done_flag());
-    } else {
-      if (bits)
-        dev::vn_update_kernel<dev::TraitsF16, true><<<grid_vnb, dev::kThreads, smem_tab, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G, done_flag());
-      else
-        dev::vn_update_kernel<dev::TraitsF16, false><<<grid_vn, dev::kThreads, smem_tab, stream>>>(
-            msg, l0, d_col_ptr.p, d_in_to_out.p, hard, d_phi_table.p, N, log2G, done_flag());
-    }
+    (bits ? k_vnb : k_vn)<<<bits ? grid_vnb : grid_vn, dev::kThreads, smem_tab, stream>>>(
+        reinterpret_cast<uint4 *>(d_msg.p), reinterpret_cast<const uint4 *>(d_llr0.p), d_col_ptr.p, d_in_to_out.p,
+        reinterpret_cast<uint8_t *>(d_hard.p), d_phi_table.p, tab_last, N, log2G, done_flag());
   }
   void launch_check() {
     cudaMemsetAsync(d_viol.p, 0, sizeof(uint32_t) << log2PW, stream);
@@ -297,6 +286,45 @@ struct ldpc_b200_decoder {
 };
 
 namespace {
+
+// smallest D in {4,6,8} such that rows of degree <= D carry >= 90 % of the edges (others take the re-read path)
+int pick_reg_degree(const std::vector<uint32_t> &offsets) {
+  const size_t n = offsets.size() - 1;
+  uint64_t le4 = 0, le6 = 0;
+  const uint64_t total = offsets[n];
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t deg = offsets[i + 1] - offsets[i];
+    if (deg <= 4) le4 += deg;
+    if (deg <= 6) le6 += deg;
+  }
+  if (le4 * 10 >= total * 9) return 4;
+  if (le6 * 10 >= total * 9) return 6;
+  return 8;
+}
+
+template <class Tr> void select_for_precision(ldpc_b200_decoder *d) {
+  switch (d->deg_cn) {
+  case 4: d->k_cn = dev::cn_update_kernel<Tr, 4>; break;
+  case 6: d->k_cn = dev::cn_update_kernel<Tr, 6>; break;
+  default: d->k_cn = dev::cn_update_kernel<Tr, 8>; break;
+  }
+  switch (d->deg_vn) {
+  case 4: d->k_vn = dev::vn_update_kernel<Tr, false, 4>; d->k_vnb = dev::vn_update_kernel<Tr, true, 4>; break;
+  case 6: d->k_vn = dev::vn_update_kernel<Tr, false, 6>; d->k_vnb = dev::vn_update_kernel<Tr, true, 6>; break;
+  default: d->k_vn = dev::vn_update_kernel<Tr, false, 8>; d->k_vnb = dev::vn_update_kernel<Tr, true, 8>; break;
+  }
+}
+
+ldpc_b200_status select_kernels(ldpc_b200_decoder *d) {
+  if (d->precision == LDPC_B200_FP32) select_for_precision<dev::TraitsF32>(d);
+  else select_for_precision<dev::TraitsF16>(d);
+  if (d->smem_tab) {
+    CU_TRY(cudaFuncSetAttribute(d->k_cn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
+    CU_TRY(cudaFuncSetAttribute(d->k_vn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
+    CU_TRY(cudaFuncSetAttribute(d->k_vnb, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
+  }
+  return LDPC_B200_OK;
+}
 
 template <typename K> int occupancy_grid(K kernel, int threads, size_t smem, int n_sms, uint64_t items) {
   int per_sm = 1;
@@ -426,26 +454,27 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   dev::build_phi_table_kernel<<<dev::kPhiTableSize / 256, 256, 0, d->stream>>>(d->d_phi_table.p);
   CU_TRY(cudaGetLastError());
 
-  // persistent grids: SMs x resident CTAs
-  d->smem_tab = d->precision == LDPC_B200_FP16 ? size_t(dev::kPhiTableSize) * 2 : 0;
-  const uint64_t cn_items = uint64_t(d->M) << d->log2G, vn_items = uint64_t(d->N) << d->log2G;
-  if (d->precision == LDPC_B200_FP32) {
-    d->grid_cn = occupancy_grid(dev::cn_update_kernel<dev::TraitsF32>, dev::kThreads, 0, d->n_sms, cn_items);
-    d->grid_vn = occupancy_grid(dev::vn_update_kernel<dev::TraitsF32, false>, dev::kThreads, 0, d->n_sms, vn_items);
-    d->grid_vnb = occupancy_grid(dev::vn_update_kernel<dev::TraitsF32, true>, dev::kThreads, 0, d->n_sms, vn_items);
-  } else {
-    CU_TRY(cudaFuncSetAttribute(dev::cn_update_kernel<dev::TraitsF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(d->smem_tab)));
-    CU_TRY(cudaFuncSetAttribute(dev::vn_update_kernel<dev::TraitsF16, false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
-    CU_TRY(cudaFuncSetAttribute(dev::vn_update_kernel<dev::TraitsF16, true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
-    d->grid_cn = occupancy_grid(dev::cn_update_kernel<dev::TraitsF16>, dev::kThreads, d->smem_tab, d->n_sms, cn_items);
-    d->grid_vn = occupancy_grid(dev::vn_update_kernel<dev::TraitsF16, false>, dev::kThreads, d->smem_tab, d->n_sms,
-                                vn_items);
-    d->grid_vnb = occupancy_grid(dev::vn_update_kernel<dev::TraitsF16, true>, dev::kThreads, d->smem_tab, d->n_sms,
-                                 vn_items);
+  // only the non-zero head of the fp16 table is staged in shared memory (2e^-x underflows above x ~ 17.3)
+  if (d->precision == LDPC_B200_FP16) {
+    std::vector<uint16_t> tab(dev::kPhiTableSize);
+    CU_TRY(cudaStreamSynchronize(d->stream));
+    CU_TRY(cudaMemcpy(tab.data(), d->d_phi_table.p, tab.size() * 2, cudaMemcpyDeviceToHost));
+    uint32_t last = 0x7C00; // +inf: phi = 0; NaN patterns never reach the lookup (hmax2 removes them)
+    while (last > 0 && tab[last - 1] == 0) --last;
+    if (tab[last] != 0) last = dev::kPhiTableSize - 1;
+    d->tab_last = last;
   }
+  // persistent grids: SMs x resident CTAs
+  ldpc_b200_status st_sel = LDPC_B200_OK;
+  d->smem_tab = d->precision == LDPC_B200_FP16 ? size_t(d->tab_last / 8 + 1) * 16 : 0;
+  const uint64_t cn_items = uint64_t(d->M) << d->log2G, vn_items = uint64_t(d->N) << d->log2G;
+  d->deg_cn = pick_reg_degree(code.row_ptr());
+  d->deg_vn = pick_reg_degree(code.col_ptr());
+  st_sel = select_kernels(d.get());
+  if (st_sel != LDPC_B200_OK) return st_sel;
+  d->grid_cn = occupancy_grid(d->k_cn, dev::kThreads, d->smem_tab, d->n_sms, cn_items);
+  d->grid_vn = occupancy_grid(d->k_vn, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
+  d->grid_vnb = occupancy_grid(d->k_vnb, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
   d->grid_misc = d->n_sms * 8;
   CU_TRY(cudaStreamSynchronize(d->stream));
   *out = d.release();

@@ -27,7 +27,13 @@
 namespace ldpc_b200 {
 namespace dev {
 
-constexpr int kMaxRegDeg = 8;       // rows of this degree or less are held in registers (one read, one write)
+// Rows of degree <= D are held in registers (one read, one write per message); D is a template parameter chosen
+// per code from {4, 6, 8} (host: pick_reg_degree).  Fewer registers buy a resident CTA: measured on B200
+// (scripts/kernel_perf.py, README-shaped code) D=6 at 4 CTAs/SM is 4-9 % faster than D=8 at 3 CTAs/SM.
+#ifndef LDPC_MINBLOCKS_D4
+#define LDPC_MINBLOCKS_D4 4
+#endif
+constexpr int min_blocks_for(int D) { return D <= 4 ? LDPC_MINBLOCKS_D4 : (D <= 6 ? 4 : 3); }
 constexpr int kThreads = 256;       // CTA size of the streaming kernels
 constexpr int kPhiTableSize = 32768; // fp16 phi_abs table entries (all non-negative half bit patterns)
 
@@ -87,6 +93,7 @@ struct TraitsF32 {
   // software prefetch of the next item's indices: measured on B200 (scripts/kernel_perf.py), it only pays in the
   // fp16 variable-node pass (+3-4 %); elsewhere the extra registers cost a resident CTA
   static constexpr bool kPrefetchCN = false, kPrefetchVN = false;
+
   __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFFFFFFu; }
   __device__ static __forceinline__ uint32_t add_w(uint32_t a, uint32_t b) {
     return __float_as_uint(__uint_as_float(a) + __uint_as_float(b));
@@ -95,7 +102,7 @@ struct TraitsF32 {
     return __float_as_uint(__uint_as_float(a) - __uint_as_float(b));
   }
   // phi_abs of a word that may be negative (clamped like the reference's fmax)
-  __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *) {
+  __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *, uint32_t) {
     return __float_as_uint(phi_abs_f32(__uint_as_float(w)));
   }
   // sign word with bit set where the frame's bit is 1 (bits = low kFramesPerWord bits)
@@ -117,17 +124,20 @@ struct TraitsF16 {
   static constexpr uint32_t kSignMask = 0x80008000u;
   static constexpr bool kUsesTable = true;
   static constexpr bool kPrefetchCN = false, kPrefetchVN = true;
+
   __device__ static __forceinline__ __half2 h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
   __device__ static __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
   __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFF7FFFu; }
   // one IEEE half rounding per add/sub, as the reference's scalar __half arithmetic (flood.cu:95-99, 134-147)
   __device__ static __forceinline__ uint32_t add_w(uint32_t a, uint32_t b) { return u32(__hadd2_rn(h2(a), h2(b))); }
   __device__ static __forceinline__ uint32_t sub_w(uint32_t a, uint32_t b) { return u32(__hsub2_rn(h2(a), h2(b))); }
-  __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *tab) {
+  // `last` = index from which every table entry is zero (2e^-x underflows in half above x ~ 17.3): only
+  // [0, last] is staged in shared memory, larger indices clamp to it
+  __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *tab, uint32_t last) {
     // negative / NaN preimages clamp to the table's first entry (flood.cu:10, 26)
     const uint32_t c = u32(__hmax2(h2(w), h2(0u)));
-    const uint32_t lo = tab[c & 0x7FFFu];
-    const uint32_t hi = tab[(c >> 16) & 0x7FFFu];
+    const uint32_t lo = tab[min(c & 0x7FFFu, last)];
+    const uint32_t hi = tab[min(c >> 16, last)];
     return lo | (hi << 16);
   }
   __device__ static __forceinline__ uint32_t sign_from_bits(uint32_t bits) {
@@ -166,12 +176,13 @@ __global__ void phi_abs_f32_kernel(const float *x, float *y, size_t n) {
   if (i < n) y[i] = phi_abs_f32(x[i]);
 }
 
-template <class Tr> __device__ __forceinline__ const uint16_t *stage_phi_table(const uint16_t *g_table) {
+template <class Tr>
+__device__ __forceinline__ const uint16_t *stage_phi_table(const uint16_t *g_table, uint32_t last) {
   if (Tr::kUsesTable) {
     extern __shared__ __align__(16) uint16_t s_table[];
     const uint4 *src = reinterpret_cast<const uint4 *>(g_table);
     uint4 *dst = reinterpret_cast<uint4 *>(s_table);
-    for (int i = threadIdx.x; i < kPhiTableSize * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < int(last / 8 + 1); i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
     return s_table;
   }
@@ -192,13 +203,13 @@ template <class Tr> __device__ __forceinline__ uint32_t load_frame_bits(const ui
 // sign = sign(m_e) xor parity, parity = syndrome bit xor (number of non-negative inputs) (flood.cu:77-115).
 // The row offsets and syndrome bits of the thread's NEXT item are fetched while the current row's messages are
 // in flight, so the dependent index -> message load chain is off the critical path.
-template <class Tr>
-__global__ void __launch_bounds__(kThreads)
+template <class Tr, int kMaxRegDeg>
+__global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
     cn_update_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
-                     const uint16_t *__restrict__ phi_table, uint32_t n_checks, uint32_t log2_g,
+                     const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
                      const uint32_t *__restrict__ done) {
   if (done && *done) return; // the device-side scheduler has retired every frame: run-ahead launches are no-ops
-  const uint16_t *tab = stage_phi_table<Tr>(phi_table);
+  const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
   const uint32_t G = 1u << log2_g;
   const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
   const uint64_t total = uint64_t(n_checks) << log2_g;
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const uint32_t mw = word(m[k], w);
-            const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab);
+            const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
             word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
           }
           st_stream(p + (size_t(k) << log2_g), o);
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           const uint32_t mw = word(mk, w);
-          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab);
+          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
           word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
         }
         st_stream(p + (size_t(k) << log2_g), o);
@@ -294,14 +305,14 @@ __global__ void __launch_bounds__(kThreads)
 // One thread = (variable v, frame vector g).  T = llr0 + sum of incoming c2v in CSC order; every edge gets
 // phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).
 // The gather list of the thread's NEXT item is fetched while the current messages are in flight.
-template <class Tr, bool kFinalBits>
-__global__ void __launch_bounds__(kThreads)
+template <class Tr, bool kFinalBits, int kMaxRegDeg>
+__global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
     vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ col_ptr,
                      const uint32_t *__restrict__ in_to_out, uint8_t *__restrict__ hard,
-                     const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t log2_g,
+                     const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_vars, uint32_t log2_g,
                      const uint32_t *__restrict__ done) {
   if (done && *done) return;
-  const uint16_t *tab = stage_phi_table<Tr>(phi_table);
+  const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
   const uint32_t G = 1u << log2_g;
   const size_t hard_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
   const uint64_t total = uint64_t(n_vars) << log2_g;
@@ -358,7 +369,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const uint32_t pre = Tr::sub_w(word(T, w), word(m[k], w));
-            const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab);
+            const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
             word(o, w) = (r & ~Tr::kSignMask) | (pre & Tr::kSignMask);
           }
           st_stream(msg + (size_t(rows[k]) << log2_g) + g, o);
@@ -384,7 +395,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           const uint32_t pre = Tr::sub_w(word(T, w), word(mk, w));
-          const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab);
+          const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
           word(o, w) = (r & ~Tr::kSignMask) | (pre & Tr::kSignMask);
         }
         st_stream(pk, o);
