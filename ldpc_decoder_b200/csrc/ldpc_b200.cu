@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -218,6 +219,25 @@ struct ldpc_b200_decoder {
   }
   const uint32_t *done_flag() const { return &d_state.p->done; }
 
+  // Staging for host-resident buffers is allocated on first use: a decoder fed from device memory never pays for
+  // the pinned mirror (N*P*s bytes) nor the device ring.
+  ldpc_b200_status ensure_input_staging() {
+    const size_t P_ = P;
+    if (!d_stage.p) CU_TRY(d_stage.alloc(size_t(N) * P_ * elem));
+    if (!h_stage.p) CU_TRY(h_stage.alloc(size_t(N) * P_ * elem));
+    return LDPC_B200_OK;
+  }
+  ldpc_b200_status ensure_syndrome_staging() {
+    if (!d_stage_syn.p) CU_TRY(d_stage_syn.alloc(size_t(S) * P));
+    if (!h_stage_syn.p) CU_TRY(h_stage_syn.alloc(size_t(S) * P));
+    return LDPC_B200_OK;
+  }
+  ldpc_b200_status ensure_result_staging() {
+    if (!d_results.p) CU_TRY(d_results.alloc(size_t(W) * P));
+    if (!h_results.p) CU_TRY(h_results.alloc(size_t(W) * P));
+    return LDPC_B200_OK;
+  }
+
   // ---- launches -----------------------------------------------------------
   // kernel instantiations are chosen once per decoder (precision, register-resident degree D)
   typedef void (*cn_fn)(uint4 *, const uint32_t *, const uint8_t *, const uint16_t *, uint32_t, uint32_t, uint32_t,
@@ -366,7 +386,10 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, d->device));
   d->n_sms = prop.multiProcessorCount;
-  d->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  // host worker threads for the staging gather; ranks of one node share the cores (torchrun exports LOCAL_WORLD_SIZE)
+  unsigned local_world = 1;
+  if (const char *lw = std::getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(lw));
+  d->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency() / local_world));
   d->precision = cfg->precision;
   d->elem = cfg->precision == LDPC_B200_FP32 ? 4 : 2;
   d->M = uint32_t(code.n_outputs());
@@ -406,15 +429,12 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   CU_TRY(cudaMemcpy(d->d_edge_var.p, code.out_edge_to_var().data(), 4ull * d->E, cudaMemcpyHostToDevice));
   CU_TRY(d->d_msg.alloc(size_t(d->E) * P * d->elem));
   CU_TRY(d->d_llr0.alloc(size_t(d->N) * P * d->elem));
-  CU_TRY(d->d_stage.alloc(size_t(d->N) * P * d->elem));
   CU_TRY(d->d_syn.alloc(size_t(d->M) << d->log2PW));
   CU_TRY(d->d_hard.alloc(size_t(d->N) << d->log2PW));
   CU_TRY(d->d_viol.alloc(P / 32));
-  CU_TRY(d->d_stage_syn.alloc(size_t(d->S) * P));
   CU_TRY(d->d_retire_mask.alloc(P / 32));
   CU_TRY(d->d_new_mask.alloc(P / 32));
   CU_TRY(d->d_slot_entry.alloc(P));
-  CU_TRY(d->d_results.alloc(size_t(d->W) * P));
   CU_TRY(d->d_refill.alloc(P));
   CU_TRY(d->d_extract.alloc(P));
   CU_TRY(d->d_phi_table.alloc(dev::kPhiTableSize));
@@ -431,10 +451,7 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   CU_TRY(cudaMemset(d->d_llr0.p, 0, size_t(d->N) * P * d->elem));
   CU_TRY(cudaMemset(d->d_syn.p, 0, (size_t(d->M) << d->log2PW) * 4));
   CU_TRY(cudaMemset(d->d_hard.p, 0, (size_t(d->N) << d->log2PW) * 4));
-  CU_TRY(d->h_stage.alloc(size_t(d->N) * P * d->elem));
-  CU_TRY(d->h_stage_syn.alloc(size_t(d->S) * P));
   CU_TRY(d->h_viol.alloc(P / 32));
-  CU_TRY(d->h_results.alloc(size_t(d->W) * P));
   CU_TRY(d->h_mask.alloc(P / 32));
   CU_TRY(d->h_retire_mask.alloc(P / 32));
   CU_TRY(d->h_slot_entry.alloc(P));
@@ -519,6 +536,14 @@ ldpc_b200_status stage_frames(ldpc_b200_decoder *d, const input_view &in, uint32
                               ldpc_b200_report *rep) {
   const uint32_t n_reg = d->N - d->n_erased;
   const size_t es = d->elem;
+  if (!in.on_device) {
+    const ldpc_b200_status se = d->ensure_input_staging();
+    if (se != LDPC_B200_OK) return se;
+  }
+  if (!in.syn_on_device) {
+    const ldpc_b200_status se = d->ensure_syndrome_staging();
+    if (se != LDPC_B200_OK) return se;
+  }
   for (uint32_t t = 0; t < cnt; ++t) {
     const uint32_t col = (first + t) % in.n_cols;
     dev::RefillEntry &en = d->h_refill.p[t];
@@ -595,6 +620,10 @@ ldpc_b200_status stage_frames(ldpc_b200_decoder *d, const input_view &in, uint32
 ldpc_b200_status retire_frames(ldpc_b200_decoder *d, uint32_t cnt, const uint32_t *slots, const uint32_t *frames,
                                uint32_t *results, bool results_on_device, ldpc_b200_report *rep) {
   const uint32_t PW = 1u << d->log2PW;
+  if (!results_on_device) {
+    const ldpc_b200_status se = d->ensure_result_staging();
+    if (se != LDPC_B200_OK) return se;
+  }
   std::fill(d->h_retire_mask.p, d->h_retire_mask.p + PW, 0u);
   for (uint32_t t = 0; t < cnt; ++t) {
     const uint32_t s = slots[t];
@@ -678,6 +707,18 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   sc.results_ring = res_dev ? 0u : 1u;
   if (!in_dev && ring_frames < std::min<uint32_t>(d->P, B + ring_block) && ring_frames < B)
     return fail(LDPC_B200_ERR_INVALID, "staging ring too small (internal error)");
+  if (!in_dev) {
+    const ldpc_b200_status se = d->ensure_input_staging();
+    if (se != LDPC_B200_OK) return se;
+  }
+  if (!syn_dev) {
+    const ldpc_b200_status se = d->ensure_syndrome_staging();
+    if (se != LDPC_B200_OK) return se;
+  }
+  if (!res_dev) {
+    const ldpc_b200_status se = d->ensure_result_staging();
+    if (se != LDPC_B200_OK) return se;
+  }
   const void *src_dev = in_dev ? input : static_cast<const void *>(d->d_stage.p);
   const uint32_t *syn_src_dev = syn_dev ? syndromes : d->d_stage_syn.p;
   uint32_t *res_dst_dev = res_dev ? results : d->d_results.p;

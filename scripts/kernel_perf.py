@@ -5,8 +5,13 @@ import numpy as np
 import ldpc_decoder_b200 as L
 from ldpc_decoder_b200 import alist, harness
 
-configs = sys.argv[1:] or ["fp16:10", "fp16:12", "fp32:10"]
-gen = alist.make_readme_shaped_code(20, seed=1)
+configs = [a for a in sys.argv[1:] if not a.startswith("code=")] or ["fp16:10", "fp16:12", "fp32:10"]
+code_arg = ([a[5:] for a in sys.argv[1:] if a.startswith("code=")] or ["readme:20"])[0].split(":")
+if code_arg[0] == "readme":
+    gen = alist.make_readme_shaped_code(int(code_arg[1]), seed=1)
+else:  # reg:log2n:dv:dc
+    gen = alist.make_regular_code(1 << int(code_arg[1]), int(code_arg[2]), int(code_arg[3]), seed=1)
+print("code", code_arg, "N", gen.n_vars, "M", gen.n_checks, "E", gen.n_edges, flush=True)
 code = L.Code.from_generated(gen)
 E, N, M = gen.n_edges, gen.n_vars, gen.n_checks
 for cfg in configs:
