@@ -326,3 +326,69 @@ def test_cpp_dropin_class_decodes(small_codes, tmp_path):
     r = subprocess.run([exe, small_codes["readme13"][1], "0.55"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "errors 0" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs at full size.  The oracle cannot finish these in seconds, so they are checked against the
+# reference's own sm_100 build where it can run (P*E < 2^32) and through size-independent properties otherwise.
+
+def test_config0_full_size_matches_reference_build(tmp_path):
+    """configs[0] shape: README-shaped N = 2^20 code, AWGN, `-p 8 -m 2 -i 120` (256 in flight, 512 frames, check
+    every 10).  fp16 build of the reference vs this decoder on identical inputs: decisions bit-exact, same
+    iteration statistics."""
+    if not rb.available("fp16"):
+        pytest.skip("oracle/_ref reference library not built")
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_readme_shaped_code(20, seed=1)
+    path = str(tmp_path / "readme20.alist")
+    alist.write_alist(gen, path)
+    sigma = 0.80  # the stand-in's threshold is ~0.826 (DESIGN.md section 6)
+    inp, syn, bits, prm = _frames(gen, 512, "awgn", sigma, 7, np.float16)
+    ref = rb.RefDecoder(path, "awgn", sigma, 8, "fp16")
+    assert ref.P == 256
+    rres, rrep = ref.decode(inp, syn, 120, 10)
+    ref.close()
+    dec = L.Decoder(L.Code(path=path), L.FP16, 8)
+    res, iters, rep = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=120, num_iter_check_parity=10)
+    assert np.array_equal(res, rres)
+    assert (rep["max_iter"], rep["min_iter"]) == (rrep["max_iter"], rrep["min_iter"])
+    assert rep["avg_iter"] == pytest.approx(rrep["avg_iter"], rel=1e-6)
+    assert harness.count_bit_errors(res, bits).sum() == 0
+
+
+def test_config1_shape_bsc_high_rate_fp32():
+    """configs[1] shape: rate-0.9 code on a BSC, fp32 messages, 2^10 frames in flight.  Stand-in: (3,32)-regular,
+    N = 2^20 (check degree 32 exercises the long-row path).  Property: decoded words satisfy their syndromes and
+    equal the transmitted words."""
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_regular_code(1 << 20, 3, 32, seed=4)
+    dec = L.Decoder(L.Code.from_generated(gen), L.FP32, 10)
+    assert dec.parallel_factor() == 1024
+    inp, syn, bits, prm = _frames(gen, 96, "bsc", 0.004, 3, np.float32)
+    res, iters, rep = dec.decode(L.BSC, prm, inp, syn, num_iter_max=100, pool_frames=96, n_frames=2048)
+    conv = iters < 100
+    assert conv.mean() > 0.9, conv.mean()
+    idx = np.arange(2048) % 96
+    assert np.array_equal(gen.syndrome_packed(res[conv][:128]), syn[idx[conv][:128]])
+    assert np.array_equal(res[conv], bits[idx[conv]])
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_config4_shape_regular36_n4m(prec):
+    """configs[4] shape: harness-generated regular (3,6) code, N = 2^22, AWGN just below threshold, up to 500
+    iterations (long-tail refill stress: frames in flight << frames)."""
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_regular_code(1 << 22, 3, 6, seed=6)
+    dt = np.float16 if prec == "fp16" else np.float32
+    dec = L.Decoder(L.Code.from_generated(gen), L.FP16 if prec == "fp16" else L.FP32, 6)
+    inp, syn, bits, prm = _frames(gen, 32, "awgn", 0.86, 5, dt)
+    res, iters, rep = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=500, pool_frames=32, n_frames=256)
+    conv = iters < 500
+    assert conv.mean() > 0.9, (conv.mean(), rep)
+    assert rep["max_iter"] <= 500 + 10 + 1
+    idx = np.arange(256) % 32
+    assert np.array_equal(res[conv], bits[idx[conv]])
+    assert np.array_equal(gen.syndrome_packed(res[conv][:32]), syn[idx[conv][:32]])
