@@ -109,8 +109,11 @@ typedef struct ldpc_b200_decode_params {
 enum {
   LDPC_B200_FLAG_SIMD_PAIRS = 1u,  /* refill counts rounded down to even, as the reference's OpenCL *
                                     * backend does (ldpc_decoder_gpu.cpp:623)                       */
-  LDPC_B200_FLAG_TIME_KERNELS = 2u /* bracket every check-node / variable-node launch with CUDA    *
-                                    * events on the launching stream and report cn_s / vn_s        */
+  LDPC_B200_FLAG_TIME_KERNELS = 2u, /* bracket every check-node / variable-node launch with CUDA    *
+                                     * events on the launching stream and report cn_s / vn_s        *
+                                     * (implies plain launches instead of the CUDA graph)            */
+  LDPC_B200_FLAG_NO_GRAPH = 4u      /* launch the per-period kernel sequence directly instead of     *
+                                     * replaying its CUDA graph                                      */
 };
 
 typedef struct ldpc_b200_report {
@@ -129,6 +132,7 @@ typedef struct ldpc_b200_report {
   double retire_s; /* extraction of retiring frames (+ D2H when results are on host) */
   double refill_s; /* staging (+ H2D) and refill kernels of new frames               */
   uint64_t frames_refilled;
+  uint64_t graph_launches; /* CUDA-graph replays of the per-period sequence (kernels inside are counted above) */
 } ldpc_b200_report;
 
 /* decode() (ldpc_decoder_gpu.h:102-110; semantics of ldpc_decoder_gpu.cu:283-634).

@@ -16,6 +16,7 @@ AWGN, BSC, LLR = 0, 1, 2
 LAYOUT_INTERLEAVED, LAYOUT_FRAME_MAJOR = 0, 1
 FLAG_SIMD_PAIRS = 1
 FLAG_TIME_KERNELS = 2
+FLAG_NO_GRAPH = 4
 
 
 class CodeInfo(C.Structure):
@@ -42,7 +43,7 @@ class Report(C.Structure):
                 ("cn_launches", C.c_uint64), ("vn_launches", C.c_uint64), ("other_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("check_s", C.c_double), ("retire_s", C.c_double), ("refill_s", C.c_double),
-                ("frames_refilled", C.c_uint64)]
+                ("frames_refilled", C.c_uint64), ("graph_launches", C.c_uint64)]
 
 
 # every symbol include/ldpc_b200.h declares: name -> (restype, argtypes)

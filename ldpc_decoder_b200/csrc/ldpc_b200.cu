@@ -739,7 +739,11 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     CU_TRY(cudaStreamSynchronize(d->copy_stream)); // earlier copies out of the pinned mirror are done
     // ring positions being overwritten belong to frames already loaded; their refill kernels must have read them
     if (refill_recorded) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_refilled, 0));
-    const uint32_t f0 = staged, f1 = upto;
+    const uint32_t f0_all = staged, f1_all = upto;
+    // in sub-ranges, so the H2D of one chunk overlaps the host gather of the next
+    const uint32_t sub = 8 * ring_block > 256 ? 8 * ring_block : 256;
+    for (uint32_t f0 = f0_all; f0 < f1_all;) {
+    const uint32_t f1 = std::min(f1_all, (f0 / sub + 1) * sub);
     if (!in_dev) {
       if (!frame_major) {
         // the reference's prepare_vectors (ldpc_decoder_gpu.cu:199-207) in blocks of ring_block frames:
@@ -800,7 +804,9 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
         f += run;
       }
     }
-    staged = f1;
+    f0 = f1;
+    }
+    staged = f1_all;
     CU_TRY(cudaEventRecord(d->ev_staged, d->copy_stream));
     CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_staged, 0)); // the refill kernels read the ring
     return LDPC_B200_OK;
@@ -906,6 +912,14 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   };
 
   // ---- main loop: the device is always one period ahead of the host
+  struct graph_pair {
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    ~graph_pair() {
+      for (cudaGraphExec_t e : exec)
+        if (e) cudaGraphExecDestroy(e);
+    }
+  } graphs;
+  bool use_graph = !time_kernels && !(prm->flags & LDPC_B200_FLAG_NO_GRAPH);
   uint64_t period = 0;
   uint32_t next_known = B; // next_to_load as of the last summary read
   enqueue_iterations(0);
@@ -938,9 +952,47 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     // frames the next refill may need: at most B beyond what has been loaded so far
     st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, uint64_t(next_known) + B)));
     if (st != LDPC_B200_OK) return st;
-    st = enqueue_service(period);
-    if (st != LDPC_B200_OK) return st;
-    enqueue_iterations(period + 1); // run ahead: no-ops once the scheduler has set `done`
+    // service of this period + the next period's flood iterations (run ahead: no-ops once the scheduler has
+    // set `done`).  The sequence is fixed, so it is captured once per parity into a CUDA graph and replayed.
+    const int hg = int(period & 1);
+    if (use_graph && !graphs.exec[hg]) {
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        st = enqueue_service(period);
+        enqueue_iterations(period + 1);
+        const cudaError_t ce = cudaStreamEndCapture(d->stream, &g);
+        if (st != LDPC_B200_OK || ce != cudaSuccess || !g ||
+            cudaGraphInstantiate(&graphs.exec[hg], g, 0) != cudaSuccess) {
+          graphs.exec[hg] = nullptr;
+          use_graph = false; // fall back to plain launches
+        }
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        // the counters were bumped while capturing; the launch below is what actually runs
+      } else {
+        cudaGetLastError();
+        use_graph = false;
+      }
+      if (!use_graph) {
+        st = enqueue_service(period);
+        if (st != LDPC_B200_OK) return st;
+        enqueue_iterations(period + 1);
+      } else {
+        CU_TRY(cudaGraphLaunch(graphs.exec[hg], d->stream));
+        rep.graph_launches++;
+      }
+    } else if (use_graph) {
+      CU_TRY(cudaGraphLaunch(graphs.exec[hg], d->stream));
+      rep.graph_launches++;
+      rep.cn_launches += k_check;
+      rep.vn_launches += k_check;
+      rep.other_launches += 5;
+      rep.n_checks_run++;
+    } else {
+      st = enqueue_service(period);
+      if (st != LDPC_B200_OK) return st;
+      enqueue_iterations(period + 1);
+    }
     CU_TRY(cudaGetLastError());
     ++period;
     if (period > period_limit) return fail(LDPC_B200_ERR_INVALID, "scheduler made no progress (internal error)");

@@ -392,3 +392,18 @@ def test_config4_shape_regular36_n4m(prec):
     idx = np.arange(256) % 32
     assert np.array_equal(res[conv], bits[idx[conv]])
     assert np.array_equal(gen.syndrome_packed(res[conv][:32]), syn[idx[conv][:32]])
+
+
+def test_graph_replay_equals_plain_launches(small_codes):
+    """The per-period kernel sequence is replayed from a CUDA graph; plain launches must give identical results."""
+    gen, path = small_codes["readme13"]
+    inp, syn, bits, prm = _frames(gen, 200, "awgn", 0.6, 11, np.float16)
+    dec = L.Decoder(L.Code(path=path), L.FP16, 5)
+    r1, i1, rep1 = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=60)
+    r2, i2, rep2 = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=60, flags=L.FLAG_NO_GRAPH)
+    r3, i3, rep3 = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=60, flags=L.FLAG_TIME_KERNELS)
+    assert rep1["graph_launches"] > 0 and rep2["graph_launches"] == 0 and rep3["graph_launches"] == 0
+    assert np.array_equal(r1, r2) and np.array_equal(i1, i2) and np.array_equal(r1, r3) and np.array_equal(i1, i3)
+    for k in ("cn_launches", "vn_launches", "other_launches", "n_checks_run", "global_iters"):
+        assert rep1[k] == rep2[k] == rep3[k], k
+    assert rep3["cn_s"] > 0 and rep3["vn_s"] > 0
