@@ -889,6 +889,11 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     rep.n_checks_run++;
     if (time_kernels) cudaEventRecord(sev[h].ev[1], d->stream);
   };
+  // while capturing, host-visible events must be recorded as external event nodes
+  bool capturing = false;
+  auto record = [&](cudaEvent_t ev) {
+    return cudaEventRecordWithFlags(ev, d->stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+  };
   auto enqueue_service = [&](uint64_t period) -> ldpc_b200_status {
     const int h = int(period & 1);
     dev::sched_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(
@@ -897,16 +902,16 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
         d->d_summary.p);
     d->launch_extract_kernel(res_dst_dev);
     if (time_kernels) cudaEventRecord(sev[h].ev[2], d->stream);
-    CU_TRY(cudaEventRecord(d->ev_extracted[h], d->stream));
+    CU_TRY(record(d->ev_extracted[h]));
     d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param);
-    CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
+    CU_TRY(record(d->ev_refilled));
     if (time_kernels) cudaEventRecord(sev[h].ev[3], d->stream);
     CU_TRY(cudaMemcpyAsync(d->h_summary.p + h, d->d_summary.p, sizeof(dev::SchedSummary), cudaMemcpyDeviceToHost,
                            d->stream));
     if (!res_dev)
       CU_TRY(cudaMemcpyAsync(d->h_retired.p + size_t(h) * d->P, d->d_retired.p, sizeof(uint32_t) * B,
                              cudaMemcpyDeviceToHost, d->stream));
-    CU_TRY(cudaEventRecord(d->ev_period[h], d->stream));
+    CU_TRY(record(d->ev_period[h]));
     rep.other_launches += 4;
     return LDPC_B200_OK;
   };
@@ -958,8 +963,10 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     if (use_graph && !graphs.exec[hg]) {
       cudaGraph_t g = nullptr;
       if (cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        capturing = true;
         st = enqueue_service(period);
         enqueue_iterations(period + 1);
+        capturing = false;
         const cudaError_t ce = cudaStreamEndCapture(d->stream, &g);
         if (st != LDPC_B200_OK || ce != cudaSuccess || !g ||
             cudaGraphInstantiate(&graphs.exec[hg], g, 0) != cudaSuccess) {
