@@ -17,7 +17,7 @@ PRE_THRESHOLD_OPENCL = np.float32(2.0 * np.exp(-11.0))  # flood_vec2.cl:187 with
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, "ldpc_oracle.c"), os.path.join(_HERE, "ldpc_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("ldpc_oracle.c", "ldpc_oracle.h", "ldpc_cpu_fast.c", "ldpc_oracle_internal.h")]
     if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
     return _LIB_PATH
@@ -78,6 +78,7 @@ def lib():
         L.oracle_decoder_create.restype = C.c_void_p
         L.oracle_decoder_create.argtypes = [C.POINTER(_Code), C.c_int, C.c_uint32, C.c_float, C.c_void_p, C.c_int]
         L.oracle_decoder_free.argtypes = [C.c_void_p]
+        L.oracle_decoder_set_fast.argtypes = [C.c_void_p, C.c_int]
         L.oracle_refill.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p]
         L.oracle_backward.argtypes = [C.c_void_p]
         L.oracle_forward.argtypes = [C.c_void_p, C.c_int]
@@ -163,7 +164,7 @@ def phi_table_h() -> np.ndarray:
 
 class OracleDecoder:
     def __init__(self, code: OracleCode, precision=FP32, log2_frames=5, pre_threshold=PRE_THRESHOLD_CUDA,
-                 phi_table=None, n_threads=None):
+                 phi_table=None, n_threads=None, fast=False):
         self.code = code
         self.precision = precision
         self.P = 1 << log2_frames
@@ -178,6 +179,8 @@ class OracleDecoder:
                                               _p(tab) if tab is not None else None, n_threads)
         if not self._d:
             raise ValueError("This decoder only handles input sizes that are multiple of 32")
+        if fast:  # SIMD-over-frames CN/VN kernels (CPU baseline timing; fp32 only)
+            lib().oracle_decoder_set_fast(self._d, 1)
 
     def refill(self, channel, param, staged: np.ndarray, syndromes: np.ndarray):
         """staged: [n_regular, cnt] channel values (frame fastest); syndromes [cnt, S]."""

@@ -236,21 +236,7 @@ void oracle_phi_table_h(uint16_t *table) {
 }
 
 /* ------------------------------------------------------------------ decoder */
-struct oracle_decoder {
-  const oracle_code *c;
-  int precision;
-  uint32_t log2P, P;
-  int64_t S; /* ceil(M/32) */
-  float pre_threshold;
-  int n_threads;
-  /* fp32 state */
-  float *msg, *llr0, *new_llr;
-  /* fp16 state (raw half bits) */
-  uint16_t *msg_h, *llr0_h, *new_llr_h;
-  uint16_t *phi_tab; /* [32768] */
-  uint32_t *syn, *new_syn;
-  uint8_t *final_bits;
-};
+#include "ldpc_oracle_internal.h"
 
 oracle_decoder *oracle_decoder_create(const oracle_code *c, int precision, uint32_t log2_frames, float pre_threshold,
                                       const uint16_t *phi_table_h, int n_threads) {
@@ -281,6 +267,8 @@ oracle_decoder *oracle_decoder_create(const oracle_code *c, int precision, uint3
   d->final_bits = (uint8_t *)calloc(N * P, 1);
   return d;
 }
+
+void oracle_decoder_set_fast(oracle_decoder *d, int fast) { d->fast = fast; }
 
 void oracle_decoder_free(oracle_decoder *d) {
   if (!d) return;
@@ -345,6 +333,10 @@ void oracle_refill(oracle_decoder *d, int channel, float channel_param, uint32_t
 
 /* flood_backward: flood.cu:77-115 */
 void oracle_backward(oracle_decoder *d) {
+  if (d->fast && d->precision == ORACLE_FP32) {
+    oracle_fast_backward(d);
+    return;
+  }
   const oracle_code *c = d->c;
   const int64_t P = d->P, M = c->n_checks;
 #pragma omp parallel for num_threads(d->n_threads) schedule(dynamic, 64)
@@ -396,6 +388,10 @@ void oracle_backward(oracle_decoder *d) {
 
 /* flood_forward / flood_forward_w_final_bits: flood.cu:117-189 */
 void oracle_forward(oracle_decoder *d, int final_bits) {
+  if (d->fast && d->precision == ORACLE_FP32) {
+    oracle_fast_forward(d, final_bits);
+    return;
+  }
   const oracle_code *c = d->c;
   const int64_t P = d->P, N = c->n_vars;
 #pragma omp parallel for num_threads(d->n_threads) schedule(dynamic, 64)

@@ -77,6 +77,10 @@ typedef struct oracle_decoder oracle_decoder;
 oracle_decoder *oracle_decoder_create(const oracle_code *c, int precision, uint32_t log2_frames,
                                       float pre_threshold, const uint16_t *phi_table_h, int n_threads);
 void oracle_decoder_free(oracle_decoder *d);
+/* fp32 only: switch the CN/VN passes to the SIMD-over-frames kernels (ldpc_cpu_fast.c).  Same algorithm and
+ * schedule; libmvec/fast-math arithmetic, so results agree with the exact kernels to ~1e-5, not bit for bit.
+ * Used for the CPU baseline timing (what a vectorising OpenCL CPU runtime would do with flood_vec2.cl). */
+void oracle_decoder_set_fast(oracle_decoder *d, int fast);
 
 /* Kernel-level entry points (each is one reference kernel over all P slots). */
 /* transfer_vectors (ldpc_decoder_gpu.cu:218-273): stage cnt new frames, convert to LLR, refill slots [0,cnt).

@@ -163,3 +163,25 @@ def test_cpp_dropin_class_compiles_and_reports_errors(tmp_path):
                            "-Wl,-rpath," + libdir])
     r = subprocess.run([exe, "/nonexistent.alist"], capture_output=True, text=True)
     assert r.returncode == 5 and "could not be opened" in r.stderr
+
+
+def test_fast_cpu_baseline_kernels_agree_with_exact_oracle(small_codes):
+    """The SIMD-over-frames kernels timed as the CPU baseline compute the same thing as the exact oracle."""
+    gen, path = small_codes["readme13"]
+    o = ob.OracleCode(path=path)
+    inp, syn, bits = harness.make_frames(gen, 40, "awgn", 0.6, seed=3)
+    prm = harness.channel_param("awgn", 0.6)
+    n_reg = gen.n_vars - gen.n_erased
+    exact = ob.OracleDecoder(o, ob.FP32, 4, pre_threshold=ob.PRE_THRESHOLD_OPENCL)
+    fast = ob.OracleDecoder(o, ob.FP32, 4, pre_threshold=ob.PRE_THRESHOLD_OPENCL, fast=True)
+    for d in (exact, fast):
+        d.refill(ob.AWGN, prm, inp[:n_reg, :16], syn[:16])
+        for _ in range(3):
+            d.backward()
+            d.forward(True)
+    a, b = exact.messages(5), fast.messages(5)
+    assert np.allclose(a, b, rtol=2e-4, atol=1e-6)
+    assert np.array_equal(exact.deinterlace(), fast.deinterlace())
+    r1, i1, _ = exact.decode(ob.AWGN, prm, 60, 10, inp, syn, simd_pairs=True)
+    r2, i2, _ = fast.decode(ob.AWGN, prm, 60, 10, inp, syn, simd_pairs=True)
+    assert np.array_equal(i1, i2) and np.array_equal(r1, r2)
