@@ -247,6 +247,7 @@ struct ldpc_b200_decoder {
   cn_fn k_cn = nullptr;
   vn_fn k_vn = nullptr, k_vnb = nullptr;
   int deg_cn = 8, deg_vn = 8;
+  int cn_parts = 1; // > 1: check rows are split over this many lanes
   void launch_cn() {
     k_cn<<<grid_cn, dev::kThreads, smem_tab, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
                                                       reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
@@ -322,12 +323,40 @@ int pick_reg_degree(const std::vector<uint32_t> &offsets) {
   return 8;
 }
 
+// Long check rows (high-rate codes): if more than 10 % of the edges sit in rows longer than 8 and those rows
+// average >= 14 edges, split every row over the fewest lanes (2, 4 or 8, eight edges each) that hold the longest
+// row; beyond 64 keep the re-read path.  Measured (scripts/kernel_perf.py): (3,32) fp32 4.55 -> 5.33 TB/s,
+// (4,16) 5.9 TB/s; at degree 12 the second lane is half empty and the re-read path wins (5.4 vs 4.7 TB/s).
+int pick_cn_parts(const std::vector<uint32_t> &row_ptr, int max_deg) {
+  const size_t n = row_ptr.size() - 1;
+  uint64_t long_edges = 0, long_rows = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t deg = row_ptr[i + 1] - row_ptr[i];
+    if (deg > 8) {
+      long_edges += deg;
+      ++long_rows;
+    }
+  }
+  if (long_edges * 10 <= uint64_t(row_ptr[n]) || long_edges < 14 * long_rows) return 1;
+  for (int parts = 2; parts <= 8; parts *= 2)
+    if (max_deg <= 8 * parts) return parts;
+  return 1;
+}
+
 template <class Tr> void select_for_precision(ldpc_b200_decoder *d) {
+  switch (d->cn_parts) { // long check rows: one row over 2/4/8 lanes (cn_update_split_kernel)
+  case 2: d->k_cn = dev::cn_update_split_kernel<Tr, 2>; break;
+  case 4: d->k_cn = dev::cn_update_split_kernel<Tr, 4>; break;
+  case 8: d->k_cn = dev::cn_update_split_kernel<Tr, 8>; break;
+  default: break;
+  }
+  if (d->cn_parts > 1) goto vn;
   switch (d->deg_cn) {
   case 4: d->k_cn = dev::cn_update_kernel<Tr, 4>; break;
   case 6: d->k_cn = dev::cn_update_kernel<Tr, 6>; break;
   default: d->k_cn = dev::cn_update_kernel<Tr, 8>; break;
   }
+vn:
   switch (d->deg_vn) {
   case 4: d->k_vn = dev::vn_update_kernel<Tr, false, 4>; d->k_vnb = dev::vn_update_kernel<Tr, true, 4>; break;
   case 6: d->k_vn = dev::vn_update_kernel<Tr, false, 6>; d->k_vnb = dev::vn_update_kernel<Tr, true, 6>; break;
@@ -487,6 +516,11 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   const uint64_t cn_items = uint64_t(d->M) << d->log2G, vn_items = uint64_t(d->N) << d->log2G;
   d->deg_cn = pick_reg_degree(code.row_ptr());
   d->deg_vn = pick_reg_degree(code.col_ptr());
+  d->cn_parts = pick_cn_parts(code.row_ptr(), code.max_degree_out());
+  if (d->cn_parts > 1 && d->log2G < 5) { // a warp must stay inside one row: at least 32/G parts
+    d->cn_parts = std::max(d->cn_parts, 32 >> d->log2G);
+    if (d->cn_parts > 8) d->cn_parts = 1;
+  }
   st_sel = select_kernels(d.get());
   if (st_sel != LDPC_B200_OK) return st_sel;
   d->grid_cn = occupancy_grid(d->k_cn, dev::kThreads, d->smem_tab, d->n_sms, cn_items);

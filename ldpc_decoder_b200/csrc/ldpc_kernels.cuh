@@ -301,6 +301,84 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
   }
 }
 
+// ---------------------------------------------------------------- check-node pass, long rows (high-rate codes)
+// Rate >= 0.8 codes have check degrees of 16-64.  Holding such a row in one thread's registers leaves too few
+// resident threads, and the two-pass loop reads every message twice.  Here a row is split over kParts lanes of
+// the same warp: lane part l keeps edges [8l, 8l+8) in registers (one read, one write per message), the sum of
+// magnitudes is CARRIED from part to part with shuffles so the additions happen in exactly the reference's edge
+// order (flood.cu:95-99; this keeps fp16 bit-exact), and the sign parity is an xor butterfly.
+// Warp layout: lane = part * (32/kParts) + j, j indexing 32/kParts consecutive 16-byte frame vectors, so each
+// part still issues full 128-byte (kParts = 4) row segments.
+template <class Tr, int kParts>
+__global__ void __launch_bounds__(kThreads, 3)
+    cn_update_split_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr,
+                           const uint8_t *__restrict__ syn, const uint16_t *__restrict__ phi_table, uint32_t tab_last,
+                           uint32_t n_checks, uint32_t log2_g, const uint32_t *__restrict__ done) {
+  if (done && *done) return;
+  constexpr int kChunk = 8;
+  constexpr int kVecPerWarp = 32 / kParts;
+  const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
+  const uint32_t G = 1u << log2_g;
+  const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t part = lane / kVecPerWarp, j = lane % kVecPerWarp;
+  const uint32_t groups_per_row = G / kVecPerWarp; // G >= 8 >= kVecPerWarp (host guarantees)
+  const uint64_t total = uint64_t(n_checks) * groups_per_row; // warp-items
+  const uint64_t warp_stride = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t wi = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; wi < total; wi += warp_stride) {
+    const uint32_t c = uint32_t(wi / groups_per_row);
+    const uint32_t g = uint32_t(wi - uint64_t(c) * groups_per_row) * kVecPerWarp + j;
+    const uint32_t a = __ldg(row_ptr + c), deg = __ldg(row_ptr + c + 1) - a;
+    const uint32_t k0 = part * kChunk; // this lane's edges: [k0, min(deg, k0 + 8))
+    uint4 *p = msg + (size_t(a + k0) << log2_g) + g;
+    uint4 m[kChunk];
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+      if (k0 + k < deg) m[k] = ld_stream(p + (size_t(k) << log2_g));
+    const uint32_t sbits = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
+    const uint32_t odd = (deg & 1u) ? Tr::kSignMask : 0u;
+    uint4 S = make_uint4(0, 0, 0, 0), X = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+      if (k0 + k < deg) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) word(X, w) ^= word(m[k], w);
+      }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+#pragma unroll
+      for (int d = kVecPerWarp; d < 32; d <<= 1) word(X, w) ^= __shfl_xor_sync(0xFFFFFFFFu, word(X, w), d);
+      word(X, w) ^= Tr::sign_from_bits(sbits >> (w * Tr::kFramesPerWord)) ^ odd;
+    }
+    // carried sum: part 0 adds its magnitudes, hands S to part 1, ... -> sequential order of the reference
+#pragma unroll
+    for (int q = 0; q < kParts; ++q) {
+      if (part == uint32_t(q)) {
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k0 + k < deg) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) word(S, w) = Tr::add_w(word(S, w), Tr::abs_w(word(m[k], w)));
+          }
+      }
+#pragma unroll
+      for (int w = 0; w < 4; ++w) word(S, w) = __shfl_sync(0xFFFFFFFFu, word(S, w), q * kVecPerWarp + j);
+    }
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+      if (k0 + k < deg) {
+        uint4 o;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t mw = word(m[k], w);
+          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
+          word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+        }
+        st_stream(p + (size_t(k) << log2_g), o);
+      }
+  }
+}
+
 // ---------------------------------------------------------------- variable-node pass
 // One thread = (variable v, frame vector g).  T = llr0 + sum of incoming c2v in CSC order; every edge gets
 // phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).
