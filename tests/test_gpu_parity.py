@@ -407,3 +407,28 @@ def test_graph_replay_equals_plain_launches(small_codes):
     for k in ("cn_launches", "vn_launches", "other_launches", "n_checks_run", "global_iters"):
         assert rep1[k] == rep2[k] == rep3[k], k
     assert rep3["cn_s"] > 0 and rep3["vn_s"] > 0
+
+
+def test_fer_ber_and_iteration_statistics_match_reference_build():
+    """north_star parity item 3: FER/BER and iteration statistics agree with the reference within 95 % CIs, at a
+    noise level where a sizeable fraction of frames fails (scripts/fer_compare.py; profiles/r01_fer_compare.json)."""
+    if not (rb.available("fp32") and rb.available("fp16")):
+        pytest.skip("oracle/_ref reference library not built")
+    import importlib.util
+    import os
+
+    from conftest import ROOT
+
+    spec = importlib.util.spec_from_file_location("fer_compare", os.path.join(ROOT, "scripts", "fer_compare.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.run(log2n=15, n_frames=768, sigma=0.83, imax=120, log2p=8)
+    for prec, r in out.items():
+        lo_n, hi_n = r["fer_ci95_new"]
+        lo_r, hi_r = r["fer_ci95_ref"]
+        assert lo_n <= r["fer_ref"] <= hi_n and lo_r <= r["fer_new"] <= hi_r, (prec, r)
+        assert 0.02 < r["fer_ref"] < 0.98, r["fer_ref"]  # the test is only meaningful away from 0 and 1
+        assert abs(r["iter_new"]["avg"] - r["iter_ref"]["avg"]) <= 0.02 * r["iter_ref"]["avg"]
+        assert abs(r["ber_new"] - r["ber_ref"]) <= 0.05 * r["ber_ref"] + 1e-7
+        if prec == "fp16":
+            assert r["frames_with_identical_decisions"] == 1.0 and r["iter_new"] == r["iter_ref"]
