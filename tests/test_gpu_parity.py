@@ -432,3 +432,30 @@ def test_fer_ber_and_iteration_statistics_match_reference_build():
         assert abs(r["ber_new"] - r["ber_ref"]) <= 0.05 * r["ber_ref"] + 1e-7
         if prec == "fp16":
             assert r["frames_with_identical_decisions"] == 1.0 and r["iter_new"] == r["iter_ref"]
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_cli_matches_the_reference_command_line_program(prec):
+    """the B200 CLI takes the reference's flags, generates the reference's frames (ChaCha8 streams keyed
+    by frame index) and prints the reference's summary; run next to the reference's own binary (sm_100 build)."""
+    import importlib.util
+    import os
+
+    from conftest import ROOT
+
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", f"ref_ldpc_decoder_cuda_{prec}")
+    new_bin = os.path.join(ROOT, "ldpc_decoder_b200", "ldpc_decoder_b200_cli")
+    if not (os.path.exists(ref_bin) and os.path.exists(new_bin)):
+        pytest.skip("CLI binaries not built")
+    spec = importlib.util.spec_from_file_location("cli_compare", os.path.join(ROOT, "scripts", "cli_compare.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r, n, rt, nt = mod.run(14, 0.80, prec, extra=("-p", "5", "-m", "4", "-e", "15", "-i", "60", "-s", "1000"))
+    assert r["frames"] == n["frames"] == "128"
+    assert r["description"] == n["description"], (r["description"], n["description"])
+    for k in ("errors", "ber", "max_err", "fer_target", "fer_any", "iters", "mbits"):
+        if prec == "fp16" or k in ("mbits",):
+            assert r[k] == n[k], (k, r[k], n[k])
+    if prec == "fp32":  # decisions can differ on frames that do not converge
+        assert abs(int(r["fer_any"]) - int(n["fer_any"])) <= 2
+        assert r["iters"].split("/")[:2] == n["iters"].split("/")[:2]
