@@ -85,6 +85,10 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code, const ldpc
 void ldpc_b200_decoder_destroy(ldpc_b200_decoder *dec);
 /* parallel_factor() (ldpc_decoder_gpu.h:120-123) */
 uint32_t ldpc_b200_decoder_frames_in_flight(const ldpc_b200_decoder *dec);
+/* Allocate the pinned staging mirror, the device ring and the result ring used when decode() is given HOST buffers
+ * (otherwise they are allocated by the first such call).  The reference allocates its pinned buffers in the
+ * constructor (ldpc_decoder_gpu.cu:119-129); the C++ class calls this from its constructor for the same reason. */
+ldpc_b200_status ldpc_b200_decoder_prepare_host_io(ldpc_b200_decoder *dec);
 /* set_erased_variables() (ldpc_decoder_gpu.h:125-128) */
 void ldpc_b200_decoder_set_erased_vars(ldpc_b200_decoder *dec, uint32_t n_erased);
 

@@ -120,6 +120,9 @@ class Decoder:
     def parallel_factor(self) -> int:
         return int(_lib.lib().ldpc_b200_decoder_frames_in_flight(self._h))
 
+    def prepare_host_io(self):
+        _check(_lib.lib().ldpc_b200_decoder_prepare_host_io(self._h))
+
     def set_erased_variables(self, n: int):
         _lib.lib().ldpc_b200_decoder_set_erased_vars(self._h, n)
 

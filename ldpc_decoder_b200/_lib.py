@@ -59,6 +59,7 @@ SYMBOLS = {
     "ldpc_b200_decoder_destroy": (None, [C.c_void_p]),
     "ldpc_b200_decoder_frames_in_flight": (C.c_uint32, [C.c_void_p]),
     "ldpc_b200_decoder_set_erased_vars": (None, [C.c_void_p, C.c_uint32]),
+    "ldpc_b200_decoder_prepare_host_io": (C.c_int, [C.c_void_p]),
     "ldpc_b200_decode": (C.c_int, [C.c_void_p, C.POINTER(DecodeParams), C.c_uint32, _VP, _VP, _VP,
                                    C.POINTER(Report), _VP]),
     "ldpc_b200_debug_refill": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_uint32, _VP, _VP]),

@@ -540,6 +540,15 @@ void ldpc_b200_decoder_destroy(ldpc_b200_decoder *dec) {
 
 uint32_t ldpc_b200_decoder_frames_in_flight(const ldpc_b200_decoder *dec) { return dec ? dec->frames_in_flight : 0; }
 
+ldpc_b200_status ldpc_b200_decoder_prepare_host_io(ldpc_b200_decoder *dec) {
+  if (!dec) return fail(LDPC_B200_ERR_INVALID, "null decoder");
+  CU_TRY(cudaSetDevice(dec->device));
+  ldpc_b200_status st = dec->ensure_input_staging();
+  if (st == LDPC_B200_OK) st = dec->ensure_syndrome_staging();
+  if (st == LDPC_B200_OK) st = dec->ensure_result_staging();
+  return st;
+}
+
 void ldpc_b200_decoder_set_erased_vars(ldpc_b200_decoder *dec, uint32_t n_erased) {
   if (dec && n_erased <= dec->N) dec->n_erased = n_erased;
 }

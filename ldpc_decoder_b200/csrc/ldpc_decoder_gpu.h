@@ -79,6 +79,7 @@ public:
     const ldpc_b200_status st = ldpc_b200_decoder_create(code, &cfg, &m_dec);
     ldpc_b200_code_destroy(code); // the decoder copied the tables (as the reference does, ldpc_decoder_gpu.cu:34-65)
     check(st);
+    check(ldpc_b200_decoder_prepare_host_io(m_dec)); // this API is always fed from host arrays
     m_parallel_factor = ldpc_b200_decoder_frames_in_flight(m_dec);
   }
   ~ldpc_decoder_gpu() { ldpc_b200_decoder_destroy(m_dec); }
