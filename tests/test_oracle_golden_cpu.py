@@ -10,7 +10,7 @@ from ldpc_decoder_b200 import harness
 from oracle import binding as ob
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(f).startswith("harness_"))
 TABLE = os.path.join(HERE, "golden", "phi_table_fp16.npy")
 
 
