@@ -791,16 +791,26 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       if (!frame_major) {
         // the reference's prepare_vectors (ldpc_decoder_gpu.cu:199-207) in blocks of ring_block frames:
         // pinned[blk][i][0..ring_block) <- input[i][col..col+run)
+        // chunk descriptors are the same for every variable row: compute them once
+        struct chunk_t {
+          size_t dst, src, bytes; // dst: offset of row 0 inside the pinned mirror; src: byte offset inside a row
+        };
+        std::vector<chunk_t> chunks;
+        for (uint32_t f = f0; f < f1;) {
+          const uint32_t r = f % ring_frames, in_blk = r % ring_block, col = f % n_cols;
+          const uint32_t run = std::min({f1 - f, ring_block - in_blk, n_cols - col});
+          chunks.push_back({(size_t(r / ring_block) * n_reg * ring_block + in_blk) * es, size_t(col) * es, size_t(run) * es});
+          f += run;
+        }
+        const size_t row_dst_stride = size_t(ring_block) * es, row_src_stride = size_t(n_cols) * es;
         parallel_for(n_reg, d->host_threads, [&](size_t ia, size_t ib) {
           for (size_t i = ia; i < ib; ++i) {
-            const uint8_t *row = in_host + i * size_t(n_cols) * es;
-            uint32_t f = f0;
-            while (f < f1) {
-              const uint32_t r = f % ring_frames, in_blk = r % ring_block, col = f % n_cols;
-              const uint32_t run = std::min({f1 - f, ring_block - in_blk, n_cols - col});
-              uint8_t *dst = d->h_stage.p + ((size_t(r / ring_block) * n_reg + i) * ring_block + in_blk) * es;
-              memcpy(dst, row + size_t(col) * es, size_t(run) * es);
-              f += run;
+            const uint8_t *row = in_host + i * row_src_stride;
+            uint8_t *dst_row = d->h_stage.p + i * row_dst_stride;
+            for (const chunk_t &c : chunks) {
+              if (c.bytes == 64) memcpy(dst_row + c.dst, row + c.src, 64); // constant sizes inline to vector moves
+              else if (c.bytes == 128) memcpy(dst_row + c.dst, row + c.src, 128);
+              else memcpy(dst_row + c.dst, row + c.src, c.bytes);
             }
           }
         });
