@@ -459,3 +459,46 @@ def test_cli_matches_the_reference_command_line_program(prec):
     if prec == "fp32":  # decisions can differ on frames that do not converge
         assert abs(int(r["fer_any"]) - int(n["fer_any"])) <= 2
         assert r["iters"].split("/")[:2] == n["iters"].split("/")[:2]
+
+
+def test_llr_input_erased_override_and_argument_checks(small_codes):
+    """decoding_input_is_llr() path (caller already converted), set_erased_variables(), frames-in-flight clamp and
+    argument validation of the C ABI."""
+    import ctypes as C
+
+    from ldpc_decoder_b200 import _lib
+
+    gen, path = small_codes["readme13"]
+    code = L.Code(path=path)
+    inp, syn, bits, prm = _frames(gen, 40, "awgn", 0.55, 21, np.float32)
+    dec = L.Decoder(code, L.FP32, 4)
+    res, iters, _ = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=80)
+    # the same frames handed over as LLRs (x * 2/sigma^2 computed by the caller, channel.llr())
+    llr = (inp * np.float32(prm)).astype(np.float32)
+    res2, iters2, _ = dec.decode(L.LLR, 0.0, llr, syn, num_iter_max=80)
+    assert np.array_equal(res, res2) and np.array_equal(iters, iters2)
+    # set_erased_variables(): treating fewer variables as punctured reads more of the input (zeros there): same result
+    # here because the punctured rows of `inp` are zero, but the priors must now come from the input array
+    dec.set_erased_variables(gen.n_erased - 32)
+    res3, iters3, _ = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=80)
+    assert np.array_equal(res, res3)
+    inp_mod = inp.copy()
+    inp_mod[gen.n_vars - gen.n_erased:gen.n_vars - gen.n_erased + 32] = 50.0 * (2 * np.unpackbits(
+        bits.view(np.uint8), axis=1, bitorder="little")[:, gen.n_vars - gen.n_erased:gen.n_vars - gen.n_erased + 32].T - 1.0)
+    res4, iters4, _ = dec.decode(L.AWGN, prm, inp_mod, syn, num_iter_max=80)  # genie priors on 32 formerly punctured bits
+    assert harness.count_bit_errors(res4, bits).sum() == 0 and iters4.mean() <= iters.mean()
+    dec.set_erased_variables(gen.n_erased)
+    # frames in flight are capped at 2^13 slots and by memory
+    big = L.Decoder(L.Code(path=small_codes["tiny"][1]), L.FP16, 20)
+    assert big.parallel_factor() == 8192
+    # argument validation
+    lib = _lib.lib()
+    prm_s = _lib.DecodeParams(channel=0, channel_param=1.0, num_iter_max=10, num_iter_check_parity=0)
+    rep = _lib.Report()
+    x = np.zeros(4, np.float32)
+    p = x.ctypes.data_as(C.c_void_p)
+    assert lib.ldpc_b200_decode(dec._h, C.byref(prm_s), 1, p, p, p, C.byref(rep), None) == _lib.ERR_INVALID
+    prm_s.num_iter_check_parity = 10
+    assert lib.ldpc_b200_decode(dec._h, C.byref(prm_s), 1, None, p, p, C.byref(rep), None) == _lib.ERR_INVALID
+    assert lib.ldpc_b200_decode(None, C.byref(prm_s), 1, p, p, p, C.byref(rep), None) == _lib.ERR_INVALID
+    assert lib.ldpc_b200_decode(dec._h, C.byref(prm_s), 0, None, None, None, None, None) == _lib.OK
