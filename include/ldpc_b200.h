@@ -172,6 +172,18 @@ ldpc_b200_status ldpc_b200_phi_table_fp16(ldpc_b200_decoder *dec, uint16_t *tabl
 /* element-wise phi_abs on the device, fp32 path (flood.cu:31-37) */
 ldpc_b200_status ldpc_b200_debug_phi_abs_f32(const float *x, float *y, size_t n);
 
+/* ---- on-device synthesis of test frames --------------------------------------------------- */
+/* Generates, in DEVICE memory, the frames the reference harness would generate on the host for absolute frame
+ * indices start_idx .. start_idx+n_frames-1 (src/main.cpp:450-538: ChaCha8 streams keyed by the frame index, random
+ * words, BPSK, channel noise, punctured tail = 0, syndromes = H x), ready to be passed to ldpc_b200_decode().
+ *   channel: LDPC_B200_AWGN (noise = sigma) or LDPC_B200_BSC (noise = flip probability)
+ *   d_input     llr_t[N * n_frames], element [v + n_frames*i]     (float, or half when the decoder is FP16)
+ *   d_syndromes u32[n_frames * ceil(M/32)] frame-major
+ *   d_ref_bits  u32[n_frames * N/32] frame-major, LSB first (the transmitted words, to count errors against) */
+ldpc_b200_status ldpc_b200_synthesize_frames(ldpc_b200_decoder *dec, int32_t channel, float noise, uint64_t start_idx,
+                                             uint32_t n_frames, void *d_input, uint32_t *d_syndromes,
+                                             uint32_t *d_ref_bits);
+
 /* algorithmic bytes of one flood iteration of ONE frame: (4E+N)*s + 4*ceil(M/32) */
 uint64_t ldpc_b200_bytes_per_frame_iteration(const ldpc_b200_decoder *dec);
 

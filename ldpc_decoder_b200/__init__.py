@@ -152,6 +152,12 @@ class Decoder:
                                            _ptr(results), C.byref(rep), _ptr(iters)))
         return results, iters, {k: getattr(rep, k) for k, _ in _lib.Report._fields_}
 
+    def synthesize_frames(self, channel: int, noise: float, start_idx: int, n_frames: int, d_input, d_syndromes,
+                          d_ref_bits):
+        """Fill CUDA tensors with the reference harness' frames start_idx.. (generated on the device)."""
+        _check(_lib.lib().ldpc_b200_synthesize_frames(self._h, channel, noise, start_idx, n_frames, _ptr(d_input),
+                                                      _ptr(d_syndromes), _ptr(d_ref_bits)))
+
     # ---- kernel-level entry points (parity tests / profiling) ----
     def refill(self, channel, channel_param, staged, syndromes):
         staged = np.ascontiguousarray(staged, dtype=self.np_dtype)

@@ -73,6 +73,7 @@ SYMBOLS = {
     "ldpc_b200_debug_read_hard": (C.c_int, [C.c_void_p, C.c_uint32, _VP]),
     "ldpc_b200_phi_table_fp16": (C.c_int, [C.c_void_p, _VP]),
     "ldpc_b200_debug_phi_abs_f32": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "ldpc_b200_synthesize_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
     "ldpc_b200_bytes_per_frame_iteration": (C.c_uint64, [C.c_void_p]),
     "ldpc_b200_last_error": (C.c_char_p, []),
     "ldpc_b200_version": (C.c_char_p, []),

@@ -9,6 +9,7 @@
 
 #include "ldpc_code.h"
 #include "ldpc_kernels.cuh"
+#include "ldpc_synth.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -1222,6 +1223,39 @@ ldpc_b200_status ldpc_b200_phi_table_fp16(ldpc_b200_decoder *d, uint16_t *table)
   if (!d || !table) return fail(LDPC_B200_ERR_INVALID, "null argument");
   CU_TRY(cudaSetDevice(d->device));
   CU_TRY(cudaMemcpy(table, d->d_phi_table.p, dev::kPhiTableSize * 2, cudaMemcpyDeviceToHost));
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_synthesize_frames(ldpc_b200_decoder *d, int32_t channel, float noise, uint64_t start_idx,
+                                             uint32_t n_frames, void *d_input, uint32_t *d_syndromes,
+                                             uint32_t *d_ref_bits) {
+  if (!d || !d_input || !d_syndromes || !d_ref_bits) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  if (channel != LDPC_B200_AWGN && channel != LDPC_B200_BSC) return fail(LDPC_B200_ERR_INVALID, "unknown channel");
+  if (n_frames == 0) return LDPC_B200_OK;
+  if (!is_device_pointer(d_input) || !is_device_pointer(d_syndromes) || !is_device_pointer(d_ref_bits))
+    return fail(LDPC_B200_ERR_INVALID, "synthesize_frames writes device memory");
+  CU_TRY(cudaSetDevice(d->device));
+  const uint32_t n_groups = (n_frames + 31) / 32;
+  dev_buf<uint32_t> sliced, syn_sliced;
+  CU_TRY(sliced.alloc(size_t(d->N) * n_groups));
+  CU_TRY(syn_sliced.alloc(size_t(d->M) * n_groups));
+  const uint64_t n_blocks = uint64_t((d->N + 15) / 16) * n_groups;
+  dev::synth_bits_kernel<<<unsigned((n_blocks + 255) / 256), 256, 0, d->stream>>>(sliced.p, start_idx, d->N, n_groups);
+  const uint32_t n_tx = d->N - d->n_erased;
+  if (d->elem == 4)
+    dev::synth_noise_kernel<float><<<(n_frames + 63) / 64, 64, 0, d->stream>>>(
+        sliced.p, static_cast<float *>(d_input), d_ref_bits, start_idx, n_frames, d->N, n_tx, n_groups, channel, noise);
+  else
+    dev::synth_noise_kernel<__half><<<(n_frames + 63) / 64, 64, 0, d->stream>>>(
+        sliced.p, static_cast<__half *>(d_input), d_ref_bits, start_idx, n_frames, d->N, n_tx, n_groups, channel, noise);
+  const uint64_t n_syn = uint64_t(d->M) * n_groups;
+  dev::synth_syndrome_kernel<<<unsigned((n_syn + 255) / 256), 256, 0, d->stream>>>(sliced.p, syn_sliced.p, d->d_row_ptr.p,
+                                                                                 d->d_edge_var.p, d->M, n_groups);
+  const uint64_t n_warps = uint64_t(d->S) * n_groups;
+  dev::synth_syndrome_transpose_kernel<<<unsigned((n_warps * 32 + 255) / 256), 256, 0, d->stream>>>(
+      syn_sliced.p, d_syndromes, d->M, n_groups, n_frames, d->S);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(d->stream));
   return LDPC_B200_OK;
 }
 

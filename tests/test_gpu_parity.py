@@ -502,3 +502,54 @@ def test_llr_input_erased_override_and_argument_checks(small_codes):
     assert lib.ldpc_b200_decode(dec._h, C.byref(prm_s), 1, None, p, p, C.byref(rep), None) == _lib.ERR_INVALID
     assert lib.ldpc_b200_decode(None, C.byref(prm_s), 1, p, p, p, C.byref(rep), None) == _lib.ERR_INVALID
     assert lib.ldpc_b200_decode(dec._h, C.byref(prm_s), 0, None, None, None, None, None) == _lib.OK
+
+
+@pytest.mark.parametrize("prec,channel,noise", [("fp32", "awgn", 0.8), ("fp16", "awgn", 0.8), ("fp32", "bsc", 0.03)])
+def test_on_device_frame_synthesis_matches_the_cpu_generator(small_codes, prec, channel, noise):
+    """frames generated on the GPU equal the frames the (reference-pinned) CPU generator makes for the
+    same absolute frame indices: transmitted words, syndromes and BSC outputs bit for bit; AWGN samples up to the
+    last-ulp difference between CUDA's and glibc's logf."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    import torch
+
+    from conftest import ROOT
+
+    gen, path = small_codes["readme13"]
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "ldpc_decoder_b200", "csrc", "harness")])
+    H = C.CDLL(os.path.join(ROOT, "ldpc_decoder_b200", "libldpc_b200_harness.so"))
+    n, start = 70, 12345
+    kind = 0 if channel == "bsc" else 1
+    fp16 = prec == "fp16"
+    N, M = gen.n_vars, gen.n_checks
+    W, S = N // 32, (M + 31) // 32
+    noisy = np.zeros((N, n), np.float16 if fp16 else np.float32)
+    ref = np.zeros((n, W), np.uint32)
+    syn = np.zeros((n, S), np.uint32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert H.ldpc_b200_harness_create_data(path.encode(), kind, C.c_float(noise), start, n, 0, int(fp16), P(noisy), P(ref),
+                                           P(syn)) == 0
+    dec = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, 5)
+    d_in = torch.zeros((N, n), dtype=torch.float16 if fp16 else torch.float32, device="cuda")
+    d_syn = torch.zeros((n, S), dtype=torch.int32, device="cuda")
+    d_ref = torch.zeros((n, W), dtype=torch.int32, device="cuda")
+    dec.synthesize_frames(L.BSC if channel == "bsc" else L.AWGN, noise, start, n, d_in, d_syn, d_ref)
+    assert np.array_equal(d_ref.cpu().numpy().view(np.uint32), ref)
+    assert np.array_equal(d_syn.cpu().numpy().view(np.uint32), syn)
+    got = d_in.cpu().numpy()
+    if channel == "bsc":
+        assert np.array_equal(got, noisy)
+    else:
+        same = (got == noisy).mean()
+        assert same > 0.99, same
+        assert np.allclose(got.astype(np.float32), noisy.astype(np.float32), rtol=2e-3 if fp16 else 1e-5, atol=1e-6)
+    # and the synthesized frames decode
+    prm = harness.channel_param(channel, noise if channel == "bsc" else float(np.float16(noise)) if fp16 else noise)
+    d_res = torch.zeros((n, W), dtype=torch.int32, device="cuda")
+    _, iters, _ = dec.decode(L.BSC if channel == "bsc" else L.AWGN, prm, d_in, d_syn, n_frames=n, num_iter_max=100,
+                             results=d_res)
+    conv = iters < 100
+    assert conv.mean() > 0.5
+    assert np.array_equal(d_res.cpu().numpy().view(np.uint32)[conv], ref[conv])
