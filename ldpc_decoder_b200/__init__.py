@@ -98,7 +98,7 @@ class Code:
         return float(np.float32(self.n_vars - self.n_checks) / np.float32(self.n_vars - self.n_erased))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:  # module globals may be gone at interpreter shutdown
             _lib.lib().ldpc_b200_code_destroy(self._h)
             self._h = None
 
@@ -204,7 +204,7 @@ class Decoder:
         return t
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.lib().ldpc_b200_decoder_destroy(self._h)
             self._h = None
 
