@@ -249,8 +249,9 @@ struct ldpc_b200_decoder {
   vn_fn k_vn = nullptr, k_vnb = nullptr;
   int deg_cn = 8, deg_vn = 8;
   int cn_parts = 1; // > 1: check rows are split over this many lanes
+  int threads_cn = dev::kThreads;
   void launch_cn() {
-    k_cn<<<grid_cn, dev::kThreads, smem_tab, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
+    k_cn<<<grid_cn, threads_cn, smem_tab, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
                                                       reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
                                                       tab_last, M, log2G, done_flag());
   }
@@ -524,7 +525,8 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   }
   st_sel = select_kernels(d.get());
   if (st_sel != LDPC_B200_OK) return st_sel;
-  d->grid_cn = occupancy_grid(d->k_cn, dev::kThreads, d->smem_tab, d->n_sms, cn_items);
+  d->threads_cn = d->cn_parts > 1 ? dev::kThreads : dev::cn_threads_for(d->deg_cn);
+  d->grid_cn = occupancy_grid(d->k_cn, d->threads_cn, d->smem_tab, d->n_sms, cn_items);
   d->grid_vn = occupancy_grid(d->k_vn, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
   d->grid_vnb = occupancy_grid(d->k_vnb, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
   d->grid_misc = d->n_sms * 8;
