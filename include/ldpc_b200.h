@@ -94,7 +94,10 @@ void ldpc_b200_decoder_set_erased_vars(ldpc_b200_decoder *dec, uint32_t n_erased
 
 enum {
   LDPC_B200_LAYOUT_INTERLEAVED = 0, /* element [v + n_frames*i] (reference API, ldpc_decoder_gpu.h:93-94) */
-  LDPC_B200_LAYOUT_FRAME_MAJOR = 1  /* element [v*frame_stride + i] (extension)         */
+  LDPC_B200_LAYOUT_FRAME_MAJOR = 1, /* element [v*frame_stride + i] (extension)         */
+  LDPC_B200_LAYOUT_PACKED_BITS = 2  /* hard-decision input, 1 bit per transmitted variable: u32 words,     *
+                                     * frame-major [v*frame_stride + i/32], bit i%32, 1 <-> +1 (extension   *
+                                     * f3: 32x less H2D than one float per bit for a BSC, main.cpp:526-527) */
 };
 
 typedef struct ldpc_b200_decode_params {
@@ -103,7 +106,8 @@ typedef struct ldpc_b200_decode_params {
   uint32_t num_iter_max;          /* m_num_iter_max          (default 100)                            */
   uint32_t num_iter_check_parity; /* m_num_iter_check_parity (default 10)                             */
   int32_t input_layout;           /* LDPC_B200_LAYOUT_*                                               */
-  uint64_t frame_stride;          /* FRAME_MAJOR: elements between frames; 0 -> N - n_erased          */
+  uint64_t frame_stride;          /* FRAME_MAJOR / PACKED_BITS: elements (words) between frames;      *
+                                   * 0 -> N - n_erased (resp. its word count)                          */
   uint32_t input_pool_frames;     /* 0: input holds n_frames frames.  k>0: input/syndromes hold k      *
                                    * frames and frame f reads column f % k (benchmark recycling pool)  */
   uint32_t flags;                 /* LDPC_B200_FLAG_*                                                  */

@@ -13,7 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OK, ERR_INVALID, ERR_CODE, ERR_MULTIPLE_32, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_ALIST = range(8)
 FP32, FP16 = 0, 1
 AWGN, BSC, LLR = 0, 1, 2
-LAYOUT_INTERLEAVED, LAYOUT_FRAME_MAJOR = 0, 1
+LAYOUT_INTERLEAVED, LAYOUT_FRAME_MAJOR, LAYOUT_PACKED_BITS = 0, 1, 2
 FLAG_SIMD_PAIRS = 1
 FLAG_TIME_KERNELS = 2
 FLAG_NO_GRAPH = 4

@@ -266,17 +266,17 @@ struct ldpc_b200_decoder {
                                                                         d_viol.p, M, log2PW, done_flag());
   }
   // refill kernels: entries, count, masks are already in device memory (scheduler kernel or host upload)
-  void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param) {
+  void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param, int packed = 0) {
     const uint32_t n_regular = N - n_erased;
     uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p), *l0 = reinterpret_cast<uint4 *>(d_llr0.p);
     if (precision == LDPC_B200_FP32)
       dev::refill_kernel<dev::TraitsF32><<<grid_misc, dev::kThreads, 0, stream>>>(
           msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p, d_col_ptr.p, d_in_to_out.p, nullptr, N,
-          n_regular, log2G, channel, param);
+          n_regular, log2G, channel, param, packed);
     else
       dev::refill_kernel<dev::TraitsF16><<<grid_misc, dev::kThreads, 0, stream>>>(
           msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p, d_col_ptr.p, d_in_to_out.p,
-          d_phi_table.p, N, n_regular, log2G, channel, param);
+          d_phi_table.p, N, n_regular, log2G, channel, param, packed);
     dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
                                                                          d_new_mask.p, d_slot_entry.p, M, log2PW);
   }
@@ -741,8 +741,12 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   sc.res_words = d->W;
   sc.n_cols = n_cols;
   sc.n_regular = n_reg;
-  sc.frame_stride = prm->frame_stride ? prm->frame_stride : n_reg;
-  const bool frame_major = prm->input_layout == LDPC_B200_LAYOUT_FRAME_MAJOR;
+  const bool packed = prm->input_layout == LDPC_B200_LAYOUT_PACKED_BITS;
+  const uint32_t row_elems = packed ? (n_reg + 31) / 32 : n_reg; // per-frame elements of a frame-major input
+  const size_t es_fm = packed ? 4 : es;                          //  ... and their size
+  sc.row_elems = row_elems;
+  sc.frame_stride = prm->frame_stride ? prm->frame_stride : row_elems;
+  const bool frame_major = prm->input_layout == LDPC_B200_LAYOUT_FRAME_MAJOR || packed;
   const uint32_t ring_block = frame_major ? 1u : 32u; // frames per interleaved staging block (64-128 B runs)
   // live staged frames are always inside [next_to_load, next_to_load + B) (+ block rounding)
   const uint32_t ring_frames = std::min<uint32_t>(d->P, ((B + ring_block - 1) / ring_block + 1) * ring_block);
@@ -833,14 +837,14 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
         parallel_for(f1 - f0, d->host_threads, [&](size_t a, size_t b2) {
           for (size_t t = a; t < b2; ++t) {
             const uint32_t f = f0 + uint32_t(t);
-            memcpy(d->h_stage.p + size_t(f % ring_frames) * n_reg * es,
-                   in_host + size_t(f % n_cols) * sc.frame_stride * es, size_t(n_reg) * es);
+            memcpy(d->h_stage.p + size_t(f % ring_frames) * row_elems * es_fm,
+                   in_host + size_t(f % n_cols) * sc.frame_stride * es_fm, size_t(row_elems) * es_fm);
           }
         });
         uint32_t f = f0;
         while (f < f1) {
           const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
-          const size_t off = size_t(r) * n_reg * es, bytes = size_t(run) * n_reg * es;
+          const size_t off = size_t(r) * row_elems * es_fm, bytes = size_t(run) * row_elems * es_fm;
           CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
           rep.h2d_bytes += bytes;
           f += run;
@@ -919,7 +923,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   dev::sched_init_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(sc, d->d_state.p, d->d_in_gpu.p, d->d_virt.p,
                                                                   d_iter_start, d_iter_end, d->d_refill.p, d->d_n_new.p,
                                                                   d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p);
-  d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param);
+  d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed);
   CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
   refill_recorded = true;
   rep.other_launches += 3;
@@ -959,7 +963,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     d->launch_extract_kernel(res_dst_dev);
     if (time_kernels) cudaEventRecord(sev[h].ev[2], d->stream);
     CU_TRY(record(d->ev_extracted[h]));
-    d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param);
+    d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed);
     CU_TRY(record(d->ev_refilled));
     if (time_kernels) cudaEventRecord(sev[h].ev[3], d->stream);
     CU_TRY(cudaMemcpyAsync(d->h_summary.p + h, d->d_summary.p, sizeof(dev::SchedSummary), cudaMemcpyDeviceToHost,

@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(kThreads)
                   const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
                   const uint32_t *__restrict__ col_ptr, const uint32_t *__restrict__ in_to_out,
                   const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t n_regular, uint32_t log2_g,
-                  int channel, float param) {
+                  int channel, float param, int packed_bits) {
   if (*n_new_ptr == 0) return; // written by the scheduler kernel (or the host for kernel-level calls)
   constexpr int V = Tr::kFramesPerVec;
   constexpr uint32_t kFull = (1u << V) - 1u;
@@ -565,16 +565,24 @@ __global__ void __launch_bounds__(kThreads)
       if ((nm >> j) & 1u) {
         const RefillEntry en = entries[__ldg(slot_entry + g * V + j)];
         const uint64_t at = en.src_offset + uint64_t(i) * en.src_stride;
+        // packed hard-decision input (1 bit per transmitted variable, frame-major words): bit 1 <-> +1
+        uint32_t pbit = 0;
+        if (packed_bits && i < n_regular)
+          pbit = (__ldg(static_cast<const uint32_t *>(src) + en.src_offset + (i >> 5)) >> (i & 31u)) & 1u;
         if (V == 4) {
           uint32_t raw = 0;
-          if (i < n_regular) raw = TraitsF32::to_llr(__ldg(static_cast<const uint32_t *>(src) + at), channel, param);
+          if (i < n_regular)
+            raw = TraitsF32::to_llr(packed_bits ? (pbit ? 0x3F800000u : 0xBF800000u)
+                                                : __ldg(static_cast<const uint32_t *>(src) + at), channel, param);
           const uint32_t r = __float_as_uint(phi_abs_f32(__uint_as_float(raw & 0x7FFFFFFFu)));
           word(L, j & 3) = raw;
           word(O, j & 3) = (r & 0x7FFFFFFFu) | (raw & 0x80000000u);
           word(SEL, j & 3) = 0xFFFFFFFFu;
         } else {
           uint32_t raw = 0;
-          if (i < n_regular) raw = TraitsF16::to_llr(__ldg(static_cast<const uint16_t *>(src) + at), channel, param);
+          if (i < n_regular)
+            raw = TraitsF16::to_llr(packed_bits ? uint16_t(pbit ? 0x3C00u : 0xBC00u)
+                                                : __ldg(static_cast<const uint16_t *>(src) + at), channel, param);
           const uint32_t r = __ldg(phi_table + (raw & 0x7FFFu));
           const uint32_t o = (r & 0x7FFFu) | (raw & 0x8000u);
           const int sh = (j & 1) * 16;
@@ -689,7 +697,7 @@ struct SchedConst {
   uint32_t ring_frames, ring_block, n_regular;
   uint32_t syn_ring;     // syndromes staged in a ring (position f % ring_frames) instead of read in place
   uint32_t results_ring; // results go to a [P][W] device ring (host drains it) instead of results[frame]
-  uint32_t pad;
+  uint32_t row_elems;    // staged elements per frame in the frame-major ring (n_regular, or its word count when packed)
   uint64_t frame_stride;
 };
 struct SchedState {
@@ -712,7 +720,7 @@ __device__ __forceinline__ void make_refill_entry(const SchedConst &c, uint32_t 
     en.src_offset = uint64_t(r / c.ring_block) * c.n_regular * c.ring_block + (r % c.ring_block);
     en.src_stride = c.ring_block;
   } else {
-    en.src_offset = uint64_t(frame % c.ring_frames) * c.n_regular;
+    en.src_offset = uint64_t(frame % c.ring_frames) * c.row_elems;
     en.src_stride = 1;
   }
   en.syn_offset = uint64_t(c.syn_ring ? frame % c.ring_frames : col) * c.syn_words;

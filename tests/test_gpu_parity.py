@@ -553,3 +553,29 @@ def test_on_device_frame_synthesis_matches_the_cpu_generator(small_codes, prec, 
     conv = iters < 100
     assert conv.mean() > 0.5
     assert np.array_equal(d_res.cpu().numpy().view(np.uint32)[conv], ref[conv])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_packed_bit_input_equals_float_input(small_codes, prec):
+    """a BSC output is one bit per variable; the packed-bit layout (32x less H2D than a float per bit)
+    decodes exactly like the reference layout."""
+    import torch
+
+    gen, path = small_codes["reg36"]
+    fp16 = prec == "fp16"
+    dt = np.float16 if fp16 else np.float32
+    inp, syn, bits, prm = _frames(gen, 150, "bsc", 0.04, 8, dt)
+    dec = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, 5)
+    res, iters, rep = dec.decode(L.BSC, prm, inp, syn, num_iter_max=60)
+    n_tx = gen.n_vars - gen.n_erased
+    hard = (inp[:n_tx] > 0).T  # [frames, n_tx]
+    pad = np.zeros((hard.shape[0], (n_tx + 31) // 32 * 32), dtype=np.uint8)
+    pad[:, :n_tx] = hard
+    packed = np.packbits(pad, axis=1, bitorder="little").view(np.uint32)
+    res2, iters2, rep2 = dec.decode(L.BSC, prm, packed, syn, n_frames=150, num_iter_max=60, layout=L.LAYOUT_PACKED_BITS)
+    assert np.array_equal(res, res2) and np.array_equal(iters, iters2)
+    assert rep2["h2d_bytes"] < rep["h2d_bytes"] / 4
+    d_packed = torch.from_numpy(packed.view(np.int32)).cuda()
+    res3, iters3, _ = dec.decode(L.BSC, prm, d_packed, syn, n_frames=150, num_iter_max=60, layout=L.LAYOUT_PACKED_BITS)
+    assert np.array_equal(res, res3) and np.array_equal(iters, iters3)
+    assert harness.count_bit_errors(res, bits)[iters < 60].sum() == 0
