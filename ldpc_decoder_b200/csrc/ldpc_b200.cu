@@ -269,14 +269,18 @@ struct ldpc_b200_decoder {
   void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param, int packed = 0) {
     const uint32_t n_regular = N - n_erased;
     uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p), *l0 = reinterpret_cast<uint4 *>(d_llr0.p);
-    if (precision == LDPC_B200_FP32)
-      dev::refill_kernel<dev::TraitsF32><<<grid_misc, dev::kThreads, 0, stream>>>(
-          msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p, d_col_ptr.p, d_in_to_out.p, nullptr, N,
-          n_regular, log2G, channel, param, packed);
-    else
-      dev::refill_kernel<dev::TraitsF16><<<grid_misc, dev::kThreads, 0, stream>>>(
-          msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p, d_col_ptr.p, d_in_to_out.p,
-          d_phi_table.p, N, n_regular, log2G, channel, param, packed);
+    auto launch = [&](auto kernel, const uint16_t *table) {
+      kernel<<<grid_misc, dev::kThreads, 0, stream>>>(msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p,
+                                                      d_col_ptr.p, d_in_to_out.p, table, N, n_regular, log2G, channel,
+                                                      param);
+    };
+    if (precision == LDPC_B200_FP32) {
+      if (packed) launch(dev::refill_kernel<dev::TraitsF32, true>, nullptr);
+      else launch(dev::refill_kernel<dev::TraitsF32, false>, nullptr);
+    } else {
+      if (packed) launch(dev::refill_kernel<dev::TraitsF16, true>, d_phi_table.p);
+      else launch(dev::refill_kernel<dev::TraitsF16, false>, d_phi_table.p);
+    }
     dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
                                                                          d_new_mask.p, d_slot_entry.p, M, log2PW);
   }

@@ -540,14 +540,15 @@ struct RefillEntry {     // one new frame
 // one new slot is rewritten whole: read 16 B, replace the new lanes, write 16 B -- for the prior row and for
 // every edge row of the variable.  prior = llr(channel value) (0 for punctured variables), edges get phi(prior)
 // (flood.cu:47-75, 297-323).  Vectors without new slots are skipped; a vector of only new slots is not read.
-template <class Tr>
+template <class Tr, bool kPacked>
 __global__ void __launch_bounds__(kThreads)
     refill_kernel(uint4 *__restrict__ msg, uint4 *__restrict__ llr0, const void *__restrict__ src,
                   const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
                   const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
                   const uint32_t *__restrict__ col_ptr, const uint32_t *__restrict__ in_to_out,
                   const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t n_regular, uint32_t log2_g,
-                  int channel, float param, int packed_bits) {
+                  int channel, float param) {
+  constexpr bool packed_bits = kPacked;
   if (*n_new_ptr == 0) return; // written by the scheduler kernel (or the host for kernel-level calls)
   constexpr int V = Tr::kFramesPerVec;
   constexpr uint32_t kFull = (1u << V) - 1u;
