@@ -340,10 +340,13 @@ def main():
             "data": "synthetic", "config": workload_config(args, gen, P),
             "avg_iter": float(np.mean([r["avg_iter"] for r in reps])),
             "decoding_throughput_mbps": gen.n_vars / MBIT / (np.mean([r["avg_iter"] for r in reps]) * (cn_s + vn_s) / (n_cn * P)),
+            # the same throughput as a fraction of the HBM roofline: frames/s <= peak / (B_it * avg_iter)
+            "roofline_mbps": peak * 1e9 / (dec.bytes_per_frame_iteration() * float(np.mean([r["avg_iter"] for r in reps]))) * world * gen.n_vars / MBIT,
             "frames_checked": int(len(sel)), "syndromes_satisfied": ok, "bit_errors_checked": int(err.sum()),
             "frac_converged": float(conv.mean()),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        line["value_over_roofline"] = line["value"] / line["roofline_mbps"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
