@@ -523,6 +523,8 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   d->deg_cn = pick_reg_degree(code.row_ptr());
   d->deg_vn = pick_reg_degree(code.col_ptr());
   d->cn_parts = pick_cn_parts(code.row_ptr(), code.max_degree_out());
+  if (const char *e = std::getenv("LDPC_B200_DEG_VN")) d->deg_vn = atoi(e); // kernel experiments only
+  if (const char *e = std::getenv("LDPC_B200_DEG_CN")) d->deg_cn = atoi(e);
   if (d->cn_parts > 1 && d->log2G < 5) { // a warp must stay inside one row: at least 32/G parts
     d->cn_parts = std::max(d->cn_parts, 32 >> d->log2G);
     if (d->cn_parts > 8) d->cn_parts = 1;
