@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--check-every", type=int, default=10)
     ap.add_argument("--pool", type=int, default=128, help="distinct synthetic frames (recycled)")
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames of the bounded CPU sample")
+    ap.add_argument("--early-retire", action="store_true",
+                    help="EXTENSION: LDPC_B200_FLAG_EARLY_RETIRE (not the reference's end-of-input behaviour)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     return ap.parse_args()
@@ -177,6 +179,7 @@ def workload_config(args, gen, P):
         "sigma": args.sigma, "num_iter_max": args.imax, "check_every": args.check_every,
         "frames_in_flight": P, "loading_factor": args.loading, "frames_per_step": (P or 0) * args.loading,
         "precision": args.precision, "frame_pool": args.pool,
+        "end_of_input": "early retire + slot compaction (extension)" if args.early_retire else "reference (all slots iterate until the last frame stops)",
         "l2": "working set (messages) >> L2 (126 MB): no flush needed between steps",
     }
 
@@ -234,13 +237,16 @@ def main():
     h_res = np.zeros((n_frames, W), dtype=np.uint32)
     torch.cuda.synchronize()
 
+    base_flags = L.FLAG_EARLY_RETIRE if args.early_retire else 0
+
     def step_device(flags=0):
         return dec.decode(L.AWGN, prm, d_in, d_syn, n_frames=n_frames, num_iter_max=args.imax,
-                          num_iter_check_parity=args.check_every, results=d_res, pool_frames=args.pool, flags=flags)
+                          num_iter_check_parity=args.check_every, results=d_res, pool_frames=args.pool,
+                          flags=flags | base_flags)
 
     def step_host():
         return dec.decode(L.AWGN, prm, inp, syn, n_frames=n_frames, num_iter_max=args.imax,
-                          num_iter_check_parity=args.check_every, results=h_res, pool_frames=args.pool)
+                          num_iter_check_parity=args.check_every, results=h_res, pool_frames=args.pool, flags=base_flags)
 
     for _ in range(args.warmup):
         step_device()

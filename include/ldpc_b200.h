@@ -120,8 +120,15 @@ enum {
   LDPC_B200_FLAG_TIME_KERNELS = 2u, /* bracket every check-node / variable-node launch with CUDA    *
                                      * events on the launching stream and report cn_s / vn_s        *
                                      * (implies plain launches instead of the CUDA graph)            */
-  LDPC_B200_FLAG_NO_GRAPH = 4u      /* launch the per-period kernel sequence directly instead of     *
+  LDPC_B200_FLAG_NO_GRAPH = 4u,     /* launch the per-period kernel sequence directly instead of     *
                                      * replaying its CUDA graph                                      */
+  LDPC_B200_FLAG_EARLY_RETIRE = 8u  /* EXTENSION (off by default; the reference keeps every slot      *
+                                     * iterating until the last frame of the call stops,              *
+                                     * ldpc_decoder_gpu.cu:419-432): once the input is exhausted, a      *
+                                     * frame is retired at the check where it stops and the frames      *
+                                     * still running are compacted into the low slots, so the tail of   *
+                                     * a call touches only as many slots as it needs.  Decisions of      *
+                                     * frames that hit num_iter_max are then taken at that check.       */
 };
 
 typedef struct ldpc_b200_report {

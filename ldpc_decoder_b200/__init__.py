@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AWGN, BSC, LLR, FP16, FP32, LAYOUT_FRAME_MAJOR, LAYOUT_INTERLEAVED, LAYOUT_PACKED_BITS, FLAG_SIMD_PAIRS, FLAG_TIME_KERNELS, FLAG_NO_GRAPH  # noqa: F401
+from ._lib import AWGN, BSC, LLR, FP16, FP32, LAYOUT_FRAME_MAJOR, LAYOUT_INTERLEAVED, LAYOUT_PACKED_BITS, FLAG_SIMD_PAIRS, FLAG_TIME_KERNELS, FLAG_NO_GRAPH, FLAG_EARLY_RETIRE  # noqa: F401
 
 
 class LdpcError(RuntimeError):

@@ -17,6 +17,7 @@ LAYOUT_INTERLEAVED, LAYOUT_FRAME_MAJOR, LAYOUT_PACKED_BITS = 0, 1, 2
 FLAG_SIMD_PAIRS = 1
 FLAG_TIME_KERNELS = 2
 FLAG_NO_GRAPH = 4
+FLAG_EARLY_RETIRE = 8
 
 
 class CodeInfo(C.Structure):

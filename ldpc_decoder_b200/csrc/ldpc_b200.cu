@@ -197,6 +197,8 @@ struct ldpc_b200_decoder {
   dev_buf<dev::SchedState> d_state;
   dev_buf<dev::SchedSummary> d_summary;
   dev_buf<uint32_t> d_n_new, d_in_gpu, d_virt, d_retired, d_iter; // d_iter: [2][n_frames] start/end, grown on demand
+  dev_buf<uint32_t> d_scratch, d_n_moves;                        // early-retire compaction
+  dev_buf<dev::SlotMove> d_moves;
   pinned_buf<dev::SchedSummary> h_summary; // [2]
   pinned_buf<uint32_t> h_retired;          // [2][P]
   cudaStream_t copy_stream = nullptr;      // H2D of new frames / D2H of results, overlapped with decoding
@@ -479,6 +481,10 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   CU_TRY(d->d_in_gpu.alloc(P));
   CU_TRY(d->d_virt.alloc(P));
   CU_TRY(d->d_retired.alloc(P));
+  CU_TRY(d->d_scratch.alloc(2 * P));
+  CU_TRY(d->d_n_moves.alloc(1));
+  CU_TRY(d->d_moves.alloc(P));
+  CU_TRY(cudaMemset(d->d_n_moves.p, 0, sizeof(uint32_t)));
   CU_TRY(cudaMemset(d->d_state.p, 0, sizeof(dev::SchedState)));
   CU_TRY(d->h_summary.alloc(2));
   CU_TRY(d->h_retired.alloc(2 * P));
@@ -759,6 +765,11 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   sc.ring_block = ring_block;
   sc.ring_frames = ring_frames;
   sc.input_mode = in_dev ? (frame_major ? 1u : 0u) : (frame_major ? 3u : 2u);
+  sc.early_retire = (prm->flags & LDPC_B200_FLAG_EARLY_RETIRE) ? 1u : 0u;
+  sc.log2_v = d->precision == LDPC_B200_FP32 ? 2u : 3u;
+  // the flood kernels need at least 32 slots, and a warp of the split-row kernel must stay inside one row
+  sc.min_log2_p_active = 5;
+  if (d->cn_parts > 1) sc.min_log2_p_active = std::max<uint32_t>(5, ilog2(32u / uint32_t(d->cn_parts)) + sc.log2_v);
   sc.syn_ring = syn_dev ? 0u : 1u;
   sc.results_ring = res_dev ? 0u : 1u;
   if (!in_dev && ring_frames < std::min<uint32_t>(d->P, B + ring_block) && ring_frames < B)
@@ -965,8 +976,18 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     dev::sched_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(
         sc, d->d_state.p, d->d_viol.p, d->d_in_gpu.p, d->d_virt.p, d_iter_start, d_iter_end, d->d_refill.p,
         d->d_extract.p, d->d_n_new.p, d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p, d->d_retired.p,
-        d->d_summary.p);
+        d->d_summary.p, d->d_scratch.p, d->d_moves.p, d->d_n_moves.p);
     d->launch_extract_kernel(res_dst_dev);
+    if (sc.early_retire) { // tail compaction of the frames still running (no-op unless the scheduler asked for moves)
+      if (d->elem == 4)
+        dev::move_slots_kernel<float><<<d->grid_misc, dev::kThreads, 0, d->stream>>>(
+            reinterpret_cast<float *>(d->d_msg.p), reinterpret_cast<float *>(d->d_llr0.p), d->d_syn.p, d->d_moves.p,
+            d->d_n_moves.p, d->E, d->N, d->M, d->log2P);
+      else
+        dev::move_slots_kernel<uint16_t><<<d->grid_misc, dev::kThreads, 0, d->stream>>>(
+            reinterpret_cast<uint16_t *>(d->d_msg.p), reinterpret_cast<uint16_t *>(d->d_llr0.p), d->d_syn.p,
+            d->d_moves.p, d->d_n_moves.p, d->E, d->N, d->M, d->log2P);
+    }
     if (time_kernels) cudaEventRecord(sev[h].ev[2], d->stream);
     CU_TRY(record(d->ev_extracted[h]));
     d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed);
@@ -978,7 +999,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       CU_TRY(cudaMemcpyAsync(d->h_retired.p + size_t(h) * d->P, d->d_retired.p, sizeof(uint32_t) * B,
                              cudaMemcpyDeviceToHost, d->stream));
     CU_TRY(record(d->ev_period[h]));
-    rep.other_launches += 4;
+    rep.other_launches += 4 + sc.early_retire;
     return LDPC_B200_OK;
   };
 
@@ -1059,7 +1080,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       rep.graph_launches++;
       rep.cn_launches += k_check;
       rep.vn_launches += k_check;
-      rep.other_launches += 5;
+      rep.other_launches += 5 + sc.early_retire;
       rep.n_checks_run++;
     } else {
       st = enqueue_service(period);

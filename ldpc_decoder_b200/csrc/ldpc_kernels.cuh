@@ -195,6 +195,13 @@ __device__ __forceinline__ const uint16_t *stage_phi_table(const uint16_t *g_tab
   return nullptr;
 }
 
+// control block handed to the streaming kernels: ctl[0] = done flag, ctl[1] = log2 of the active vectors per row
+// (0 = all of them)
+__device__ __forceinline__ uint32_t active_log2(const uint32_t *ctl, uint32_t log2_g) {
+  const uint32_t a = ctl ? ctl[1] : 0u;
+  return a ? a : log2_g;
+}
+
 __device__ __forceinline__ uint32_t &word(uint4 &v, int i) { return reinterpret_cast<uint32_t *>(&v)[i]; }
 __device__ __forceinline__ uint32_t word(const uint4 &v, int i) { return reinterpret_cast<const uint32_t *>(&v)[i]; }
 
@@ -216,22 +223,25 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
                      const uint32_t *__restrict__ done) {
   if (done && *done) return; // the device-side scheduler has retired every frame: run-ahead launches are no-ops
   const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
-  const uint32_t G = 1u << log2_g;
+  const uint32_t G = 1u << log2_g; // row stride in vectors
+  // active vectors per row: the scheduler may have compacted the live frames into the low slots (early retire)
+  const uint32_t log2_ga = active_log2(done, log2_g);
+  const uint32_t GA = 1u << log2_ga;
   const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
-  const uint64_t total = uint64_t(n_checks) << log2_g;
+  const uint64_t total = uint64_t(n_checks) << log2_ga;
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   uint32_t a_next = 0, b_next = 0, sbits_next = 0;
   if (Tr::kPrefetchCN && item < total) {
-    const uint32_t c = uint32_t(item >> log2_g);
+    const uint32_t c = uint32_t(item >> log2_ga);
     a_next = __ldg(row_ptr + c);
     b_next = __ldg(row_ptr + c + 1);
-    sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, uint32_t(item) & (G - 1u));
+    sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, uint32_t(item) & (GA - 1u));
   }
   for (; item < total; item += stride) {
-    const uint32_t g = uint32_t(item) & (G - 1u);
+    const uint32_t g = uint32_t(item) & (GA - 1u);
     if (!Tr::kPrefetchCN) {
-      const uint32_t c = uint32_t(item >> log2_g);
+      const uint32_t c = uint32_t(item >> log2_ga);
       a_next = __ldg(row_ptr + c);
       b_next = __ldg(row_ptr + c + 1);
       sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
       for (int k = 0; k < kMaxRegDeg; ++k)
         if (k < deg) m[k] = ld_stream(p + (size_t(k) << log2_g));
       if (Tr::kPrefetchCN && item + stride < total) { // next item's indices behind the message loads
-        const uint32_t c = uint32_t((item + stride) >> log2_g);
+        const uint32_t c = uint32_t((item + stride) >> log2_ga);
         a_next = __ldg(row_ptr + c);
         b_next = __ldg(row_ptr + c + 1);
         sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
         }
     } else {
       if (Tr::kPrefetchCN && item + stride < total) {
-        const uint32_t c = uint32_t((item + stride) >> log2_g);
+        const uint32_t c = uint32_t((item + stride) >> log2_ga);
         a_next = __ldg(row_ptr + c);
         b_next = __ldg(row_ptr + c + 1);
         sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
@@ -325,10 +335,11 @@ __global__ void __launch_bounds__(kThreads, 3)
   constexpr int kVecPerWarp = 32 / kParts;
   const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
   const uint32_t G = 1u << log2_g;
+  const uint32_t GA = 1u << active_log2(done, log2_g);
   const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t part = lane / kVecPerWarp, j = lane % kVecPerWarp;
-  const uint32_t groups_per_row = G / kVecPerWarp; // G >= 8 >= kVecPerWarp (host guarantees)
+  const uint32_t groups_per_row = GA / kVecPerWarp; // active G >= kVecPerWarp (host guarantees)
   const uint64_t total = uint64_t(n_checks) * groups_per_row; // warp-items
   const uint64_t warp_stride = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   for (uint64_t wi = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; wi < total; wi += warp_stride) {
@@ -398,14 +409,16 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
   if (done && *done) return;
   const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
   const uint32_t G = 1u << log2_g;
+  const uint32_t log2_ga = active_log2(done, log2_g);
+  const uint32_t GA = 1u << log2_ga;
   const size_t hard_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
-  const uint64_t total = uint64_t(n_vars) << log2_g;
+  const uint64_t total = uint64_t(n_vars) << log2_ga;
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   uint32_t a_next = 0, deg_next = 0;
   uint32_t rows_next[kMaxRegDeg];
   if (Tr::kPrefetchVN && item < total) {
-    const uint32_t v = uint32_t(item >> log2_g);
+    const uint32_t v = uint32_t(item >> log2_ga);
     a_next = __ldg(col_ptr + v);
     deg_next = __ldg(col_ptr + v + 1) - a_next;
 #pragma unroll
@@ -413,8 +426,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
       if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
   }
   for (; item < total; item += stride) {
-    const uint32_t v = uint32_t(item >> log2_g);
-    const uint32_t g = uint32_t(item) & (G - 1u);
+    const uint32_t v = uint32_t(item >> log2_ga);
+    const uint32_t g = uint32_t(item) & (GA - 1u);
     if (!Tr::kPrefetchVN) {
       a_next = __ldg(col_ptr + v);
       deg_next = __ldg(col_ptr + v + 1) - a_next;
@@ -433,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
         if (k < deg) m[k] = ld_stream(msg + (size_t(rows[k]) << log2_g) + g);
       }
       if (Tr::kPrefetchVN && item + stride < total) { // next item's gather list behind the message loads
-        const uint32_t vn = uint32_t((item + stride) >> log2_g);
+        const uint32_t vn = uint32_t((item + stride) >> log2_ga);
         a_next = __ldg(col_ptr + vn);
         deg_next = __ldg(col_ptr + vn + 1) - a_next;
 #pragma unroll
@@ -460,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
         }
     } else {
       if (Tr::kPrefetchVN && item + stride < total) {
-        const uint32_t vn = uint32_t((item + stride) >> log2_g);
+        const uint32_t vn = uint32_t((item + stride) >> log2_ga);
         a_next = __ldg(col_ptr + vn);
         deg_next = __ldg(col_ptr + vn + 1) - a_next;
 #pragma unroll
@@ -700,12 +713,20 @@ struct SchedConst {
   uint32_t results_ring; // results go to a [P][W] device ring (host drains it) instead of results[frame]
   uint32_t row_elems;    // staged elements per frame in the frame-major ring (n_regular, or its word count when packed)
   uint64_t frame_stride;
+  // LDPC_B200_FLAG_EARLY_RETIRE: once the input is exhausted, retire frames as soon as they stop and compact the
+  // survivors into the low slots so that the flood kernels touch only 2^log2_ga vectors per row
+  uint32_t early_retire, log2_v /* log2 frames per 16-byte vector */, min_log2_p_active, pad2;
 };
 struct SchedState {
-  uint32_t next_to_load, g, done, period;
+  uint32_t next_to_load, g;
+  uint32_t done, log2_ga; // control block read by the streaming kernels (ctl[0], ctl[1]): keep adjacent
+  uint32_t period, batch_active;
 };
 struct SchedSummary {
-  uint32_t n_new, n_retired, next_to_load, done, g, n_stop, period, pad;
+  uint32_t n_new, n_retired, next_to_load, done, g, n_stop, period, n_moves;
+};
+struct SlotMove {
+  uint32_t src, dst;
 };
 
 __device__ __forceinline__ void make_refill_entry(const SchedConst &c, uint32_t frame, uint32_t slot, RefillEntry &en) {
@@ -780,7 +801,9 @@ __global__ void __launch_bounds__(kSchedThreads)
     st->next_to_load = c.batch;
     st->g = c.k_check; // the first check happens at global iteration k (after k+1 flood iterations)
     st->done = 0;
+    st->log2_ga = 0; // all vectors of a row are live
     st->period = 0;
+    st->batch_active = c.batch;
     *n_new_out = c.batch;
   }
 }
@@ -789,12 +812,14 @@ __global__ void __launch_bounds__(kSchedThreads)
     sched_kernel(SchedConst c, SchedState *st, const uint32_t *__restrict__ viol, uint32_t *in_gpu, uint32_t *virt,
                  uint32_t *iter_start, uint32_t *iter_end, RefillEntry *entries, ExtractEntry *slot_dst,
                  uint32_t *n_new_out, uint32_t *new_mask, uint32_t *retire_mask, uint32_t *slot_entry,
-                 uint32_t *retired_frames, SchedSummary *summary) {
+                 uint32_t *retired_frames, SchedSummary *summary, uint32_t *scratch /* [2P] */, SlotMove *moves,
+                 uint32_t *n_moves_out) {
   __shared__ uint8_t s_stop[kMaxSlots];
   __shared__ uint32_t s_partner[kMaxSlots]; // finished positions >= n_new, compacted in position order
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_n_new, s_all_done;
-  const uint32_t B = c.batch, PW = (1u << c.log2_p) >> 5, tid = threadIdx.x;
+  const uint32_t B = st->batch_active, PW = (1u << c.log2_p) >> 5, tid = threadIdx.x;
+  if (tid == 0) *n_moves_out = 0;
   if (st->done) { // run-ahead period after the end: nothing to retire or load
     for (uint32_t w = tid; w < PW; w += blockDim.x) new_mask[w] = retire_mask[w] = 0;
     if (tid == 0) {
@@ -820,6 +845,95 @@ __global__ void __launch_bounds__(kSchedThreads)
       ++my_stop;
       if (iter_end[f] == 0xFFFFFFFFu) iter_end[f] = g;
     }
+  }
+  if (c.early_retire && next == c.n_frames) {
+    // ---- input exhausted, early-retire mode: every stopped frame leaves now; survivors are compacted
+    __shared__ uint32_t s_occ[kMaxSlots / 32];
+    __shared__ uint32_t s_p_new;
+    for (uint32_t w = tid; w < PW; w += blockDim.x) new_mask[w] = retire_mask[w] = 0;
+    for (uint32_t w = tid; w < kMaxSlots / 32; w += blockDim.x) s_occ[w] = 0;
+    uint32_t tot_stop;
+    uint32_t rank_stop = block_exclusive_scan(my_stop, s_warp, tot_stop);
+    uint32_t tot_keep;
+    uint32_t rank_keep = block_exclusive_scan((j1 - j0) - my_stop, s_warp, tot_keep);
+    uint32_t *keep_frame = scratch, *keep_slot = scratch + (1u << c.log2_p);
+    for (uint32_t j = j0; j < j1; ++j) {
+      const uint32_t s = virt[j], f = in_gpu[j];
+      if (s_stop[j]) {
+        const uint32_t t = rank_stop++;
+        atomicOr(retire_mask + (s >> 5), 1u << (s & 31u));
+        slot_dst[s].dst_offset = c.results_ring ? uint64_t(t) * c.res_words : uint64_t(f) * c.res_words;
+        retired_frames[t] = f;
+      } else {
+        const uint32_t k = rank_keep++;
+        keep_frame[k] = f;
+        keep_slot[k] = s;
+      }
+    }
+    __syncthreads();
+    const uint32_t Bn = tot_keep;
+    // target slot range: the smallest power of two holding the survivors (never below the kernels' minimum)
+    if (tid == 0) {
+      uint32_t lp = c.min_log2_p_active;
+      while ((1u << lp) < Bn) ++lp;
+      const uint32_t cur = st->log2_ga ? st->log2_ga + c.log2_v : c.log2_p;
+      s_p_new = lp < cur ? lp : cur;
+    }
+    __syncthreads();
+    const uint32_t log2_pn = s_p_new, Pn = 1u << log2_pn;
+    const uint32_t cur_log2_p = st->log2_ga ? st->log2_ga + c.log2_v : c.log2_p;
+    const uint32_t chunk_k = (Bn + blockDim.x - 1) / blockDim.x;
+    const uint32_t k0 = min(Bn, tid * chunk_k), k1 = min(Bn, k0 + chunk_k);
+    uint32_t n_moves = 0;
+    if (log2_pn < cur_log2_p && Bn > 0) {
+      uint32_t my_movers = 0;
+      for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t s = keep_slot[k];
+        if (s < Pn) atomicOr(s_occ + (s >> 5), 1u << (s & 31u));
+        else ++my_movers;
+      }
+      __syncthreads();
+      uint32_t tot_movers;
+      uint32_t rank_m = block_exclusive_scan(my_movers, s_warp, tot_movers);
+      // free slots below Pn, in increasing order
+      const uint32_t chunk_s = (Pn + blockDim.x - 1) / blockDim.x;
+      const uint32_t s0 = min(Pn, tid * chunk_s), s1 = min(Pn, s0 + chunk_s);
+      uint32_t my_free = 0;
+      for (uint32_t s2 = s0; s2 < s1; ++s2) my_free += !((s_occ[s2 >> 5] >> (s2 & 31u)) & 1u);
+      uint32_t tot_free;
+      uint32_t rank_f = block_exclusive_scan(my_free, s_warp, tot_free);
+      for (uint32_t s2 = s0; s2 < s1; ++s2)
+        if (!((s_occ[s2 >> 5] >> (s2 & 31u)) & 1u)) s_partner[rank_f++] = s2;
+      __syncthreads();
+      for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t s = keep_slot[k];
+        if (s >= Pn) {
+          const uint32_t dst = s_partner[rank_m];
+          moves[rank_m].src = s;
+          moves[rank_m].dst = dst;
+          keep_slot[k] = dst;
+          ++rank_m;
+        }
+      }
+      n_moves = tot_movers;
+      __syncthreads();
+    }
+    for (uint32_t k = k0; k < k1; ++k) {
+      in_gpu[k] = keep_frame[k];
+      virt[k] = keep_slot[k];
+    }
+    if (tid == 0) {
+      *n_new_out = 0;
+      *n_moves_out = n_moves;
+      st->g = g + c.k_check;
+      st->done = Bn == 0 ? 1u : 0u;
+      if (Bn > 0 && log2_pn < cur_log2_p) st->log2_ga = log2_pn - c.log2_v;
+      st->batch_active = Bn;
+      st->period = period + 1;
+      SchedSummary sm = {0, tot_stop, next, Bn == 0 ? 1u : 0u, g, tot_stop, period, n_moves};
+      *summary = sm;
+    }
+    return;
   }
   uint32_t n_stop;
   block_exclusive_scan(my_stop, s_warp, n_stop);
@@ -886,6 +1000,38 @@ __global__ void __launch_bounds__(kSchedThreads)
     st->period = period + 1;
     SchedSummary sm = {n_new, all_done ? B : n_new, next + n_new, all_done ? 1u : 0u, g, n_stop, period, 0};
     *summary = sm;
+  }
+}
+
+// Early-retire compaction: copy the state of the frames named in `moves` (src slot -> dst slot): messages, priors
+// and target-syndrome bits.  One thread = (row, move).  (The reference moves frames with flood_permute_vecs on every
+// refill, flood.cu:225-275; here it only happens in the tail of a call, for the few frames still running.)
+template <typename Elem>
+__global__ void __launch_bounds__(kThreads)
+    move_slots_kernel(Elem *__restrict__ msg, Elem *__restrict__ llr0, uint32_t *__restrict__ syn,
+                      const SlotMove *__restrict__ moves, const uint32_t *__restrict__ n_moves_ptr, uint32_t n_edges,
+                      uint32_t n_vars, uint32_t n_checks, uint32_t log2_p) {
+  const uint32_t n_moves = *n_moves_ptr;
+  if (n_moves == 0) return;
+  const uint64_t rows = uint64_t(n_edges) + n_vars + n_checks;
+  const uint64_t total = rows * n_moves;
+  const uint32_t log2_pw = log2_p - 5;
+  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
+       item += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t row = item / n_moves;
+    const SlotMove mv = moves[item - row * n_moves];
+    if (row < n_edges) {
+      msg[(size_t(row) << log2_p) + mv.dst] = msg[(size_t(row) << log2_p) + mv.src];
+    } else if (row < uint64_t(n_edges) + n_vars) {
+      const size_t v = size_t(row - n_edges);
+      llr0[(v << log2_p) + mv.dst] = llr0[(v << log2_p) + mv.src];
+    } else {
+      const size_t c = size_t(row - n_edges - n_vars);
+      const uint32_t bit = (syn[(c << log2_pw) + (mv.src >> 5)] >> (mv.src & 31u)) & 1u;
+      uint32_t *w = syn + (c << log2_pw) + (mv.dst >> 5);
+      if (bit) atomicOr(w, 1u << (mv.dst & 31u));
+      else atomicAnd(w, ~(1u << (mv.dst & 31u)));
+    }
   }
 }
 

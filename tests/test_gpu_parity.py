@@ -579,3 +579,40 @@ def test_packed_bit_input_equals_float_input(small_codes, prec):
     res3, iters3, _ = dec.decode(L.BSC, prm, d_packed, syn, n_frames=150, num_iter_max=60, layout=L.LAYOUT_PACKED_BITS)
     assert np.array_equal(res, res3) and np.array_equal(iters, iters3)
     assert harness.count_bit_errors(res, bits)[iters < 60].sum() == 0
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+@pytest.mark.parametrize("name,noise,n_frames,log2p", [("reg36", 0.78, 300, 6), ("readme13", 0.6, 200, 7), ("hideg", 0.01, 100, 6)])
+def test_early_retire_extension(small_codes, prec, name, noise, n_frames, log2p):
+    """LDPC_B200_FLAG_EARLY_RETIRE: same stop rule and iteration counts as the reference schedule; frames that
+    converged keep their decisions; the tail of the call runs on compacted slots (host and device buffers)."""
+    import torch
+
+    gen, path = small_codes[name]
+    fp16 = prec == "fp16"
+    channel = "bsc" if name == "hideg" else "awgn"
+    ch = L.BSC if channel == "bsc" else L.AWGN
+    inp, syn, bits, prm = _frames(gen, n_frames, channel, noise, 31, np.float16 if fp16 else np.float32)
+    dec = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, log2p)
+    res, iters, rep = dec.decode(ch, prm, inp, syn, num_iter_max=60)
+    res2, iters2, rep2 = dec.decode(ch, prm, inp, syn, num_iter_max=60, flags=L.FLAG_EARLY_RETIRE)
+    if fp16:
+        assert np.array_equal(iters, iters2)
+    else:
+        assert (iters == iters2).mean() > 0.97
+    conv = (iters < 60) & (iters == iters2)
+    assert conv.mean() > 0.5
+    assert np.array_equal(res[conv], res2[conv])
+    assert np.array_equal(gen.syndrome_packed(res2[conv]), syn[conv])
+    assert rep2["global_iters"] <= rep["global_iters"]
+    # device-resident buffers take the same path
+    d_in = torch.from_numpy(inp.view(np.int16) if fp16 else inp).cuda()
+    d_syn = torch.from_numpy(syn.view(np.int32)).cuda()
+    d_res = torch.zeros((n_frames, gen.n_vars // 32), dtype=torch.int32, device="cuda")
+    _, iters3, _ = dec.decode(ch, prm, d_in, d_syn, n_frames=n_frames, num_iter_max=60, results=d_res,
+                              flags=L.FLAG_EARLY_RETIRE)
+    assert np.array_equal(iters3, iters2)
+    assert np.array_equal(d_res.cpu().numpy().view(np.uint32), res2)
+    # and the decoder is reusable afterwards with the reference schedule
+    res4, iters4, _ = dec.decode(ch, prm, inp, syn, num_iter_max=60)
+    assert np.array_equal(res4, res) and np.array_equal(iters4, iters)
