@@ -286,15 +286,17 @@ def main():
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     s = 2 if args.precision == "fp16" else 4
     E, N, M = gen.n_edges, gen.n_vars, gen.n_checks
-    cn_bytes = (2 * E * s + 4 * ((M + 31) // 32)) * P  # per CN launch (all allocated slots are processed)
-    vn_bytes = ((2 * E + N) * s) * P                     # per VN launch
+    cn_bytes = (2 * E * s + 4 * ((M + 31) // 32)) * P  # per CN launch over all P slots
+    vn_bytes = ((2 * E + N) * s) * P                     # per VN launch over all P slots
     cn_s = sum(r["cn_s"] for r in reps)
     vn_s = sum(r["vn_s"] for r in reps)
     n_cn = sum(r["cn_launches"] for r in reps)
     n_vn = sum(r["vn_launches"] for r in reps)
-    cn_gbs = cn_bytes * n_cn / cn_s / 1e9
-    vn_gbs = vn_bytes * n_vn / vn_s / 1e9
-    pair_gbs = (cn_bytes * n_cn + vn_bytes * n_vn) / (cn_s + vn_s) / 1e9
+    # launches over fewer than P slots (early-retire tail) count for the slots they process
+    slot_frac = sum(r["slot_iterations"] for r in reps) / float(n_cn * P)
+    cn_gbs = cn_bytes * n_cn * slot_frac / cn_s / 1e9
+    vn_gbs = vn_bytes * n_vn * slot_frac / vn_s / 1e9
+    pair_gbs = (cn_bytes * n_cn + vn_bytes * n_vn) * slot_frac / (cn_s + vn_s) / 1e9
     dev_s = sum(r["device_s"] for r in reps)
     traffic = None
     try:
@@ -310,6 +312,7 @@ def main():
         "traffic": traffic,
         "cn": {"gbs": cn_gbs, "frac": cn_gbs / peak, "avg_ms": 1e3 * cn_s / n_cn, "bytes_per_launch": cn_bytes},
         "vn": {"gbs": vn_gbs, "frac": vn_gbs / peak, "avg_ms": 1e3 * vn_s / n_vn, "bytes_per_launch": vn_bytes},
+        "slot_fraction": slot_frac,
         "kernel_share_of_step": (cn_s + vn_s) / dev_s if dev_s else None,
         "timed": {"cn_s": cn_s, "vn_s": vn_s, "device_s": dev_s, "n_cn": int(n_cn), "n_vn": int(n_vn),
                   "global_iters": [int(r["global_iters"]) for r in reps]},

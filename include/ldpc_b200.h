@@ -148,6 +148,8 @@ typedef struct ldpc_b200_report {
   double refill_s; /* staging (+ H2D) and refill kernels of new frames               */
   uint64_t frames_refilled;
   uint64_t graph_launches; /* CUDA-graph replays of the per-period sequence (kernels inside are counted above) */
+  uint64_t slot_iterations; /* sum over flood iterations of the slots processed (P each, fewer once EARLY_RETIRE     *
+                             * has compacted the tail): x bytes per slot-iteration = algorithmic bytes moved         */
 } ldpc_b200_report;
 
 /* decode() (ldpc_decoder_gpu.h:102-110; semantics of ldpc_decoder_gpu.cu:283-634).

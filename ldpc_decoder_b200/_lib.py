@@ -44,7 +44,8 @@ class Report(C.Structure):
                 ("cn_launches", C.c_uint64), ("vn_launches", C.c_uint64), ("other_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("check_s", C.c_double), ("retire_s", C.c_double), ("refill_s", C.c_double),
-                ("frames_refilled", C.c_uint64), ("graph_launches", C.c_uint64)]
+                ("frames_refilled", C.c_uint64), ("graph_launches", C.c_uint64),
+                ("slot_iterations", C.c_uint64)]
 
 
 # every symbol include/ldpc_b200.h declares: name -> (restype, argtypes)

@@ -1014,6 +1014,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   bool use_graph = !time_kernels && !(prm->flags & LDPC_B200_FLAG_NO_GRAPH);
   uint64_t period = 0;
   uint32_t next_known = B; // next_to_load as of the last summary read
+  rep.slot_iterations = uint64_t(k_check + 1) * d->P; // period 0
   enqueue_iterations(0);
   for (;;) {
     if (period > 0) {
@@ -1040,6 +1041,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
         rep.global_iters = sm.g; // the loop index at which the reference breaks (:414-462)
         break;
       }
+      rep.slot_iterations += uint64_t(k_check) << sm.log2_p_active; // the k iterations that follow this check
     }
     // frames the next refill may need: at most B beyond what has been loaded so far
     st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, uint64_t(next_known) + B)));

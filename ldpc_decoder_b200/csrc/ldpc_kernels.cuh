@@ -724,6 +724,7 @@ struct SchedState {
 };
 struct SchedSummary {
   uint32_t n_new, n_retired, next_to_load, done, g, n_stop, period, n_moves;
+  uint32_t log2_p_active, pad[3]; // slots the flood kernels process from now on
 };
 struct SlotMove {
   uint32_t src, dst;
@@ -824,7 +825,7 @@ __global__ void __launch_bounds__(kSchedThreads)
     for (uint32_t w = tid; w < PW; w += blockDim.x) new_mask[w] = retire_mask[w] = 0;
     if (tid == 0) {
       *n_new_out = 0;
-      SchedSummary sm = {0, 0, st->next_to_load, 1, st->g, 0, st->period, 0};
+      SchedSummary sm = {0, 0, st->next_to_load, 1, st->g, 0, st->period, 0, c.log2_p, {0, 0, 0}};
       *summary = sm;
       st->period++;
     }
@@ -930,7 +931,8 @@ __global__ void __launch_bounds__(kSchedThreads)
       if (Bn > 0 && log2_pn < cur_log2_p) st->log2_ga = log2_pn - c.log2_v;
       st->batch_active = Bn;
       st->period = period + 1;
-      SchedSummary sm = {0, tot_stop, next, Bn == 0 ? 1u : 0u, g, tot_stop, period, n_moves};
+      SchedSummary sm = {0, tot_stop, next, Bn == 0 ? 1u : 0u, g, tot_stop, period, n_moves,
+                         (Bn > 0 && log2_pn < cur_log2_p) ? log2_pn : cur_log2_p, {0, 0, 0}};
       *summary = sm;
     }
     return;
@@ -998,7 +1000,8 @@ __global__ void __launch_bounds__(kSchedThreads)
     st->g = g + c.k_check;
     st->done = all_done ? 1u : 0u;
     st->period = period + 1;
-    SchedSummary sm = {n_new, all_done ? B : n_new, next + n_new, all_done ? 1u : 0u, g, n_stop, period, 0};
+    SchedSummary sm = {n_new, all_done ? B : n_new, next + n_new, all_done ? 1u : 0u, g, n_stop, period, 0,
+                       c.log2_p, {0, 0, 0}};
     *summary = sm;
   }
 }
