@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--log2-frames", type=int, default=12)
     ap.add_argument("--loading", type=int, default=8)
     ap.add_argument("--log2-n", type=int, default=20)
-    ap.add_argument("--sigma", type=float, default=0.83)
+    ap.add_argument("--sigma", type=float, default=0.824,
+                    help="AWGN sigma; the stand-in code's threshold is ~0.826 (the absent sample code: 0.95, run at 0.94)")
     ap.add_argument("--imax", type=int, default=120)
     ap.add_argument("--check-every", type=int, default=10)
     ap.add_argument("--pool", type=int, default=128, help="distinct synthetic frames (recycled)")
