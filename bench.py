@@ -177,7 +177,10 @@ def workload_config(args, gen, P):
         "workload": "BASELINE.json configs[2]: rate-0.5 AWGN code (README-shaped stand-in, the sample alist is "
                     "absent from the reference tree), fp16 messages, 2^12 frames in flight, loading factor 8",
         "code": {"n_vars": gen.n_vars, "n_checks": gen.n_checks, "n_edges": gen.n_edges, "n_punctured": gen.n_erased},
-        "sigma": args.sigma, "num_iter_max": args.imax, "check_every": args.check_every,
+        "sigma": args.sigma,
+        "sigma_note": "the stand-in ensemble's threshold is ~0.826 (the absent sample code: 0.95, README run at 0.94); "
+                      "0.824 gives converging frames with ~67 average iterations",
+        "num_iter_max": args.imax, "check_every": args.check_every,
         "frames_in_flight": P, "loading_factor": args.loading, "frames_per_step": (P or 0) * args.loading,
         "precision": args.precision, "frame_pool": args.pool,
         "end_of_input": "early retire + slot compaction (extension)" if args.early_retire else "reference (all slots iterate until the last frame stops)",
