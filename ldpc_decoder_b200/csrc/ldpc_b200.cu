@@ -252,8 +252,10 @@ struct ldpc_b200_decoder {
   int deg_cn = 8, deg_vn = 8;
   int cn_parts = 1; // > 1: check rows are split over this many lanes
   int threads_cn = dev::kThreads;
+  bool cn_bulk = false;   // experiment (LDPC_B200_CN_BULK=1): bulk-async staged check-node kernel
+  size_t smem_cn = 0;     // dynamic shared memory of the check-node kernel
   void launch_cn() {
-    k_cn<<<grid_cn, threads_cn, smem_tab, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
+    k_cn<<<grid_cn, threads_cn, smem_cn, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
                                                       reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
                                                       tab_last, M, log2G, done_flag());
   }
@@ -359,6 +361,14 @@ template <class Tr> void select_for_precision(ldpc_b200_decoder *d) {
   default: break;
   }
   if (d->cn_parts > 1) goto vn;
+  if (d->cn_bulk) { // experiment: bulk-async staged check-node kernel
+    switch (d->deg_cn) {
+    case 4: d->k_cn = dev::cn_update_bulk_kernel<Tr, 4>; break;
+    case 6: d->k_cn = dev::cn_update_bulk_kernel<Tr, 6>; break;
+    default: d->k_cn = dev::cn_update_bulk_kernel<Tr, 8>; break;
+    }
+    goto vn;
+  }
   switch (d->deg_cn) {
   case 4: d->k_cn = dev::cn_update_kernel<Tr, 4>; break;
   case 6: d->k_cn = dev::cn_update_kernel<Tr, 6>; break;
@@ -529,6 +539,9 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   d->deg_cn = pick_reg_degree(code.row_ptr());
   d->deg_vn = pick_reg_degree(code.col_ptr());
   d->cn_parts = pick_cn_parts(code.row_ptr(), code.max_degree_out());
+  if (const char *e = std::getenv("LDPC_B200_CN_BULK"))
+    d->cn_bulk = atoi(e) != 0 && d->cn_parts == 1 && code.max_degree_out() <= d->deg_cn &&
+                 (1u << d->log2G) >= uint32_t(dev::kBulkTileVec);
   if (const char *e = std::getenv("LDPC_B200_DEG_VN")) d->deg_vn = atoi(e); // kernel experiments only
   if (const char *e = std::getenv("LDPC_B200_DEG_CN")) d->deg_cn = atoi(e);
   if (d->cn_parts > 1 && d->log2G < 5) { // a warp must stay inside one row: at least 32/G parts
@@ -538,7 +551,13 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   st_sel = select_kernels(d.get());
   if (st_sel != LDPC_B200_OK) return st_sel;
   d->threads_cn = d->cn_parts > 1 ? dev::kThreads : dev::cn_threads_for(d->deg_cn);
-  d->grid_cn = occupancy_grid(d->k_cn, d->threads_cn, d->smem_tab, d->n_sms, cn_items);
+  d->smem_cn = d->smem_tab;
+  if (d->cn_bulk) {
+    d->threads_cn = dev::kBulkTileVec;
+    d->smem_cn = d->smem_tab + size_t(dev::kBulkStages) * d->deg_cn * dev::kBulkTileVec * 16 + 64;
+    CU_TRY(cudaFuncSetAttribute(d->k_cn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_cn)));
+  }
+  d->grid_cn = occupancy_grid(d->k_cn, d->threads_cn, d->smem_cn, d->n_sms, cn_items);
   d->grid_vn = occupancy_grid(d->k_vn, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
   d->grid_vnb = occupancy_grid(d->k_vnb, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
   d->grid_misc = d->n_sms * 8;
@@ -770,6 +789,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   // the flood kernels need at least 32 slots, and a warp of the split-row kernel must stay inside one row
   sc.min_log2_p_active = 5;
   if (d->cn_parts > 1) sc.min_log2_p_active = std::max<uint32_t>(5, ilog2(32u / uint32_t(d->cn_parts)) + sc.log2_v);
+  if (d->cn_bulk) sc.min_log2_p_active = ilog2(uint32_t(dev::kBulkTileVec)) + sc.log2_v; // whole tiles only
   sc.syn_ring = syn_dev ? 0u : 1u;
   sc.results_ring = res_dev ? 0u : 1u;
   if (!in_dev && ring_frames < std::min<uint32_t>(d->P, B + ring_block) && ring_frames < B)

@@ -396,6 +396,140 @@ __global__ void __launch_bounds__(kThreads, 3)
   }
 }
 
+// ---------------------------------------------------------------- check-node pass, bulk-async (TMA) staged  [EXPERIMENT]
+// Same arithmetic as cn_update_kernel, but the row slices of a tile (one check x 256 frame vectors = D x 4 KB) are
+// brought into shared memory by the bulk-copy engine (cp.async.bulk + mbarrier complete_tx), updated in place by the
+// 256 threads and written back with cp.async.bulk (bulk_group), three tiles in flight per CTA.  Selected with
+// LDPC_B200_CN_BULK=1; see DESIGN.md for the measurement that decides whether it replaces the register kernel.
+namespace bulk {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 24)) __trap(); // never hang the GPU on a protocol bug
+}
+__device__ __forceinline__ void load_bulk(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void store_bulk(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+} // namespace bulk
+
+constexpr int kBulkStages = 3;
+constexpr int kBulkTileVec = 256; // vectors (threads) per tile
+template <class Tr, int kMaxRegDeg>
+__global__ void __launch_bounds__(kBulkTileVec, 2)
+    cn_update_bulk_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
+                          const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
+                          const uint32_t *__restrict__ done) {
+  if (done && *done) return;
+  extern __shared__ __align__(16) uint16_t s_table[]; // [table | stages | barriers]
+  const uint32_t table_bytes = Tr::kUsesTable ? (tab_last / 8 + 1) * 16 : 0;
+  uint4 *stages = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(s_table) + table_bytes);
+  uint64_t *full = reinterpret_cast<uint64_t *>(stages + size_t(kBulkStages) * kMaxRegDeg * kBulkTileVec);
+  const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t G = 1u << log2_g;
+  const uint32_t GA = 1u << active_log2(done, log2_g);
+  const size_t syn_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
+  const uint32_t tiles_per_row = GA / kBulkTileVec;
+  const uint64_t total = uint64_t(n_checks) * tiles_per_row;
+  if (tid == 0)
+    for (int sidx = 0; sidx < kBulkStages; ++sidx) bulk::mbar_init(full + sidx, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  auto tile_of = [&](uint64_t i) { return uint64_t(blockIdx.x) + i * gridDim.x; };
+  auto issue = [&](uint64_t i) { // thread 0: bring tile i's rows into stage i % kBulkStages
+    const uint64_t t = tile_of(i);
+    if (t >= total) return;
+    const uint32_t c = uint32_t(t / tiles_per_row), gb = uint32_t(t - uint64_t(c) * tiles_per_row);
+    const uint32_t a = __ldg(row_ptr + c), deg = __ldg(row_ptr + c + 1) - a;
+    const int sidx = int(i % kBulkStages);
+    bulk::mbar_expect_tx(full + sidx, deg * kBulkTileVec * 16u);
+    for (uint32_t k = 0; k < deg; ++k)
+      bulk::load_bulk(stages + (size_t(sidx) * kMaxRegDeg + k) * kBulkTileVec,
+                      msg + (size_t(a + k) << log2_g) + size_t(gb) * kBulkTileVec, kBulkTileVec * 16u, full + sidx);
+  };
+  if (tid == 0)
+    for (int i = 0; i < kBulkStages - 1; ++i) issue(uint64_t(i));
+  for (uint64_t i = 0; tile_of(i) < total; ++i) {
+    const uint64_t t = tile_of(i);
+    const uint32_t c = uint32_t(t / tiles_per_row), gb = uint32_t(t - uint64_t(c) * tiles_per_row);
+    const uint32_t g = gb * kBulkTileVec + tid;
+    const uint32_t a = __ldg(row_ptr + c), deg = __ldg(row_ptr + c + 1) - a;
+    const uint32_t sbits = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
+    const int sidx = int(i % kBulkStages);
+    uint4 *tile = stages + size_t(sidx) * kMaxRegDeg * kBulkTileVec;
+    bulk::mbar_wait(full + sidx, uint32_t((i / kBulkStages) & 1));
+    const uint32_t odd = (deg & 1u) ? Tr::kSignMask : 0u;
+    uint4 S = make_uint4(0, 0, 0, 0), X;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) word(X, w) = Tr::sign_from_bits(sbits >> (w * Tr::kFramesPerWord)) ^ odd;
+    uint4 m[kMaxRegDeg];
+#pragma unroll
+    for (int k = 0; k < kMaxRegDeg; ++k)
+      if (k < deg) m[k] = tile[size_t(k) * kBulkTileVec + tid];
+#pragma unroll
+    for (int k = 0; k < kMaxRegDeg; ++k)
+      if (k < deg) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          word(S, w) = Tr::add_w(word(S, w), Tr::abs_w(word(m[k], w)));
+          word(X, w) ^= word(m[k], w);
+        }
+      }
+#pragma unroll
+    for (int k = 0; k < kMaxRegDeg; ++k)
+      if (k < deg) {
+        uint4 o;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t mw = word(m[k], w);
+          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
+          word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+        }
+        tile[size_t(k) * kBulkTileVec + tid] = o;
+      }
+    bulk::fence_async_smem(); // generic-proxy writes -> visible to the bulk-copy (async) proxy
+    __syncthreads();
+    if (tid == 0) {
+      for (uint32_t k = 0; k < deg; ++k)
+        bulk::store_bulk(msg + (size_t(a + k) << log2_g) + size_t(gb) * kBulkTileVec,
+                         tile + size_t(k) * kBulkTileVec, kBulkTileVec * 16u);
+      bulk::store_commit();
+      // the stage tile i-1 used may be refilled once its write-back has finished READING shared memory
+      bulk::store_wait_read<1>();
+      issue(i + kBulkStages - 1);
+    }
+  }
+  if (tid == 0) bulk::store_wait_all();
+}
+
 // ---------------------------------------------------------------- variable-node pass
 // One thread = (variable v, frame vector g).  T = llr0 + sum of incoming c2v in CSC order; every edge gets
 // phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).

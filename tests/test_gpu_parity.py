@@ -616,3 +616,36 @@ def test_early_retire_extension(small_codes, prec, name, noise, n_frames, log2p)
     # and the decoder is reusable afterwards with the reference schedule
     res4, iters4, _ = dec.decode(ch, prm, inp, syn, num_iter_max=60)
     assert np.array_equal(res4, res) and np.array_equal(iters4, iters)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_bulk_async_check_node_kernel_is_bit_exact(prec, monkeypatch):
+    """The experimental cp.async.bulk + mbarrier staged check-node kernel (LDPC_B200_CN_BULK=1) computes exactly what
+    the register-resident kernel computes (measured, not the default)."""
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_readme_shaped_code(14, seed=1)
+    code = L.Code.from_generated(gen)
+    fp16 = prec == "fp16"
+    log2p = 11 if fp16 else 10
+    P = 1 << log2p
+    inp, syn, bits, prm = _frames(gen, 64, "awgn", 0.8, 1, np.float16 if fp16 else np.float32)
+    n_reg = gen.n_vars - gen.n_erased
+    st, sy = np.tile(inp[:n_reg], (1, P // 64)), np.tile(syn, (P // 64, 1))
+    monkeypatch.delenv("LDPC_B200_CN_BULK", raising=False)
+    a = L.Decoder(code, L.FP16 if fp16 else L.FP32, log2p)
+    monkeypatch.setenv("LDPC_B200_CN_BULK", "1")
+    b = L.Decoder(code, L.FP16 if fp16 else L.FP32, log2p)
+    for d in (a, b):
+        d.refill(L.AWGN, prm, st, sy)
+        d.iterate(6, final_bits=True)
+    for s in (0, 7, 63, 64, P - 1):
+        assert np.array_equal(a.messages(s).view(np.uint32), b.messages(s).view(np.uint32)), s
+        assert np.array_equal(a.hard(s), b.hard(s)), s
+    # whole decode, incl. the early-retire tail (compaction must stop at whole 256-vector tiles)
+    n = 3 * P
+    res_a, it_a, _ = a.decode(L.AWGN, prm, inp, syn, n_frames=n, num_iter_max=40, pool_frames=64, flags=L.FLAG_EARLY_RETIRE)
+    res_b, it_b, _ = b.decode(L.AWGN, prm, inp, syn, n_frames=n, num_iter_max=40, pool_frames=64, flags=L.FLAG_EARLY_RETIRE)
+    assert np.array_equal(it_a, it_b)
+    conv = it_a < 40
+    assert np.array_equal(res_a[conv], res_b[conv])
