@@ -9,6 +9,15 @@ configs = [a for a in sys.argv[1:] if not a.startswith("code=")] or ["fp16:10", 
 code_arg = ([a[5:] for a in sys.argv[1:] if a.startswith("code=")] or ["readme:20"])[0].split(":")
 if code_arg[0] == "readme":
     gen = alist.make_readme_shaped_code(int(code_arg[1]), seed=1)
+elif code_arg[0] == "banded":  # banded:log2n:dv:dc:window  (locality experiment: edges stay within a window)
+    n, dv, dc, win = 1 << int(code_arg[1]), int(code_arg[2]), int(code_arg[3]), int(code_arg[4])
+    rng = np.random.default_rng(1)
+    sockets = np.repeat(np.arange(n, dtype=np.int64), dv)
+    for b in range(0, sockets.size, win):
+        blk = sockets[b:b + win]
+        sockets[b:b + win] = blk[rng.permutation(blk.size)]
+    m = n * dv // dc
+    gen = alist.Code(m, n, np.arange(0, m * dc + 1, dc, dtype=np.uint32), sockets.astype(np.uint32), 0)
 else:  # reg:log2n:dv:dc
     gen = alist.make_regular_code(1 << int(code_arg[1]), int(code_arg[2]), int(code_arg[3]), seed=1)
 print("code", code_arg, "N", gen.n_vars, "M", gen.n_checks, "E", gen.n_edges, flush=True)
