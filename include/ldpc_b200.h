@@ -150,6 +150,11 @@ typedef struct ldpc_b200_report {
   uint64_t graph_launches; /* CUDA-graph replays of the per-period sequence (kernels inside are counted above) */
   uint64_t slot_iterations; /* sum over flood iterations of the slots processed (P each, fewer once EARLY_RETIRE     *
                              * has compacted the tail): x bytes per slot-iteration = algorithmic bytes moved         */
+  /* The first check-node pass of every check period also builds the start messages of the frames loaded at that   *
+   * check (fused refill).  Those launches are included in cn_launches; their CUDA-event time is kept apart from    *
+   * cn_s so that cn_s / (cn_launches - cn_refill_launches) is the plain check-node pass.                           */
+  uint64_t cn_refill_launches;
+  double cn_refill_s;
 } ldpc_b200_report;
 
 /* decode() (ldpc_decoder_gpu.h:102-110; semantics of ldpc_decoder_gpu.cu:283-634).

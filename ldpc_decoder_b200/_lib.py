@@ -45,7 +45,7 @@ class Report(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("check_s", C.c_double), ("retire_s", C.c_double), ("refill_s", C.c_double),
                 ("frames_refilled", C.c_uint64), ("graph_launches", C.c_uint64),
-                ("slot_iterations", C.c_uint64)]
+                ("slot_iterations", C.c_uint64), ("cn_refill_launches", C.c_uint64), ("cn_refill_s", C.c_double)]
 
 
 # every symbol include/ldpc_b200.h declares: name -> (restype, argtypes)

@@ -210,7 +210,7 @@ struct ldpc_b200_decoder {
 
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-  int grid_cn = 1, grid_vn = 1, grid_vnb = 1, grid_misc = 1;
+  int grid_cn = 1, grid_cn_refill = 1, grid_vn = 1, grid_vnb = 1, grid_misc = 1;
   size_t smem_tab = 0;
   uint32_t tab_last = dev::kPhiTableSize - 1; // first index from which the fp16 phi table is all zero
 
@@ -247,7 +247,10 @@ struct ldpc_b200_decoder {
                         const uint32_t *);
   typedef void (*vn_fn)(uint4 *, const uint4 *, const uint32_t *, const uint32_t *, uint8_t *, const uint16_t *,
                         uint32_t, uint32_t, uint32_t, const uint32_t *);
+  typedef void (*cn_refill_fn)(uint4 *, const uint32_t *, const uint8_t *, const uint16_t *, uint32_t, uint32_t,
+                               uint32_t, const uint32_t *, const dev::CnRefillArgs);
   cn_fn k_cn = nullptr;
+  cn_refill_fn k_cn_refill = nullptr; // fused refill: first check-node pass of a period (null: refill writes the messages)
   vn_fn k_vn = nullptr, k_vnb = nullptr;
   int deg_cn = 8, deg_vn = 8;
   int cn_parts = 1; // > 1: check rows are split over this many lanes
@@ -258,6 +261,14 @@ struct ldpc_b200_decoder {
     k_cn<<<grid_cn, threads_cn, smem_cn, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
                                                       reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
                                                       tab_last, M, log2G, done_flag());
+  }
+  // first check-node pass after refill_kernel<.., kMsgRows = false>: start messages of the new slots come from the priors
+  void launch_cn_refill() {
+    const dev::CnRefillArgs ra{reinterpret_cast<const uint4 *>(d_llr0.p), d_edge_var.p,
+                               reinterpret_cast<const uint8_t *>(d_new_mask.p)};
+    k_cn_refill<<<grid_cn_refill, dev::kThreads, smem_tab, stream>>>(
+        reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
+        tab_last, M, log2G, done_flag(), ra);
   }
   void launch_vn(bool bits) {
     (bits ? k_vnb : k_vn)<<<bits ? grid_vnb : grid_vn, dev::kThreads, smem_tab, stream>>>(
@@ -270,7 +281,8 @@ struct ldpc_b200_decoder {
                                                                         d_viol.p, M, log2PW, done_flag());
   }
   // refill kernels: entries, count, masks are already in device memory (scheduler kernel or host upload)
-  void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param, int packed = 0) {
+  void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param, int packed = 0,
+                             bool msg_rows = true) {
     const uint32_t n_regular = N - n_erased;
     uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p), *l0 = reinterpret_cast<uint4 *>(d_llr0.p);
     auto launch = [&](auto kernel, const uint16_t *table) {
@@ -279,11 +291,15 @@ struct ldpc_b200_decoder {
                                                       param);
     };
     if (precision == LDPC_B200_FP32) {
-      if (packed) launch(dev::refill_kernel<dev::TraitsF32, true>, nullptr);
-      else launch(dev::refill_kernel<dev::TraitsF32, false>, nullptr);
+      if (packed) msg_rows ? launch(dev::refill_kernel<dev::TraitsF32, true, true>, nullptr)
+                           : launch(dev::refill_kernel<dev::TraitsF32, true, false>, nullptr);
+      else msg_rows ? launch(dev::refill_kernel<dev::TraitsF32, false, true>, nullptr)
+                    : launch(dev::refill_kernel<dev::TraitsF32, false, false>, nullptr);
     } else {
-      if (packed) launch(dev::refill_kernel<dev::TraitsF16, true>, d_phi_table.p);
-      else launch(dev::refill_kernel<dev::TraitsF16, false>, d_phi_table.p);
+      if (packed) msg_rows ? launch(dev::refill_kernel<dev::TraitsF16, true, true>, d_phi_table.p)
+                           : launch(dev::refill_kernel<dev::TraitsF16, true, false>, d_phi_table.p);
+      else msg_rows ? launch(dev::refill_kernel<dev::TraitsF16, false, true>, d_phi_table.p)
+                    : launch(dev::refill_kernel<dev::TraitsF16, false, false>, d_phi_table.p);
     }
     dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
                                                                          d_new_mask.p, d_slot_entry.p, M, log2PW);
@@ -353,7 +369,7 @@ int pick_cn_parts(const std::vector<uint32_t> &row_ptr, int max_deg) {
   return 1;
 }
 
-template <class Tr> void select_for_precision(ldpc_b200_decoder *d) {
+template <class Tr, class Idx> void select_for_precision(ldpc_b200_decoder *d) {
   switch (d->cn_parts) { // long check rows: one row over 2/4/8 lanes (cn_update_split_kernel)
   case 2: d->k_cn = dev::cn_update_split_kernel<Tr, 2>; break;
   case 4: d->k_cn = dev::cn_update_split_kernel<Tr, 4>; break;
@@ -370,26 +386,41 @@ template <class Tr> void select_for_precision(ldpc_b200_decoder *d) {
     goto vn;
   }
   switch (d->deg_cn) {
-  case 4: d->k_cn = dev::cn_update_kernel<Tr, 4>; break;
-  case 6: d->k_cn = dev::cn_update_kernel<Tr, 6>; break;
-  default: d->k_cn = dev::cn_update_kernel<Tr, 8>; break;
+  case 4: d->k_cn = dev::cn_update_kernel<Tr, 4, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 4>; break;
+  case 6: d->k_cn = dev::cn_update_kernel<Tr, 6, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 6>; break;
+  default: d->k_cn = dev::cn_update_kernel<Tr, 8, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 8>; break;
   }
 vn:
   switch (d->deg_vn) {
-  case 4: d->k_vn = dev::vn_update_kernel<Tr, false, 4>; d->k_vnb = dev::vn_update_kernel<Tr, true, 4>; break;
-  case 6: d->k_vn = dev::vn_update_kernel<Tr, false, 6>; d->k_vnb = dev::vn_update_kernel<Tr, true, 6>; break;
-  default: d->k_vn = dev::vn_update_kernel<Tr, false, 8>; d->k_vnb = dev::vn_update_kernel<Tr, true, 8>; break;
+  case 4: d->k_vn = dev::vn_update_kernel<Tr, false, 4, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 4, Idx>; break;
+  case 6: d->k_vn = dev::vn_update_kernel<Tr, false, 6, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 6, Idx>; break;
+  default: d->k_vn = dev::vn_update_kernel<Tr, false, 8, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 8, Idx>; break;
   }
 }
 
 ldpc_b200_status select_kernels(ldpc_b200_decoder *d) {
-  if (d->precision == LDPC_B200_FP32) select_for_precision<dev::TraitsF32>(d);
-  else select_for_precision<dev::TraitsF16>(d);
+  // 32-bit vector indices when every (row, vector) index of the message and prior arrays fits (see cn_update_kernel)
+  const bool idx32 = (uint64_t(std::max(d->E, d->N)) << d->log2G) < (1ull << 32) && !std::getenv("LDPC_B200_IDX64");
+  if (d->precision == LDPC_B200_FP32) {
+    if (idx32) select_for_precision<dev::TraitsF32, uint32_t>(d);
+    else select_for_precision<dev::TraitsF32, size_t>(d);
+  } else {
+    if (idx32) select_for_precision<dev::TraitsF16, uint32_t>(d);
+    else select_for_precision<dev::TraitsF16, size_t>(d);
+  }
   if (d->smem_tab) {
     CU_TRY(cudaFuncSetAttribute(d->k_cn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
     CU_TRY(cudaFuncSetAttribute(d->k_vn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
     CU_TRY(cudaFuncSetAttribute(d->k_vnb, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
+    if (d->k_cn_refill)
+      CU_TRY(cudaFuncSetAttribute(d->k_cn_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
   }
+  // EXPERIMENT, off unless LDPC_B200_FUSED_REFILL=1: refill writes only the priors and the first check-node pass of the
+  // period builds the start messages.  Measured on B200 (bench --loading 2): bit-exact, not faster -- the fused pass
+  // holds message and prior vectors of a row at once (96 registers, 2 CTAs/SM) and loses more than the skipped
+  // message-row rewrite saves.
+  const char *fused = std::getenv("LDPC_B200_FUSED_REFILL");
+  if (!fused || atoi(fused) == 0) d->k_cn_refill = nullptr;
   return LDPC_B200_OK;
 }
 
@@ -558,9 +589,10 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
     CU_TRY(cudaFuncSetAttribute(d->k_cn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_cn)));
   }
   d->grid_cn = occupancy_grid(d->k_cn, d->threads_cn, d->smem_cn, d->n_sms, cn_items);
+  if (d->k_cn_refill) d->grid_cn_refill = occupancy_grid(d->k_cn_refill, dev::kThreads, d->smem_tab, d->n_sms, cn_items);
   d->grid_vn = occupancy_grid(d->k_vn, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
   d->grid_vnb = occupancy_grid(d->k_vnb, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
-  d->grid_misc = d->n_sms * 8;
+  d->grid_misc = d->n_sms * 8; // x 256 threads: a multiple of every row length G <= 2048 (refill_kernel keeps its g)
   CU_TRY(cudaStreamSynchronize(d->stream));
   *out = d.release();
   return LDPC_B200_OK;
@@ -929,7 +961,8 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       float a = 0, b2 = 0;
       cudaEventElapsedTime(&a, tev[h].ev[3 * i], tev[h].ev[3 * i + 1]);
       cudaEventElapsedTime(&b2, tev[h].ev[3 * i + 1], tev[h].ev[3 * i + 2]);
-      rep.cn_s += a * 1e-3;
+      if (i == 0 && d->k_cn_refill) rep.cn_refill_s += a * 1e-3; // the fused pass is timed apart from the plain ones
+      else rep.cn_s += a * 1e-3;
       rep.vn_s += b2 * 1e-3;
     }
     timed_iters[h] = 0;
@@ -960,7 +993,9 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   dev::sched_init_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(sc, d->d_state.p, d->d_in_gpu.p, d->d_virt.p,
                                                                   d_iter_start, d_iter_end, d->d_refill.p, d->d_n_new.p,
                                                                   d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p);
-  d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed);
+  // fused refill: refill_kernel writes only the priors, the first check-node pass of the period makes the messages
+  const bool fused = d->k_cn_refill != nullptr;
+  d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed, !fused);
   CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
   refill_recorded = true;
   rep.other_launches += 3;
@@ -972,7 +1007,8 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     for (uint32_t i = 0; i < n_it; ++i) {
       const bool last = i + 1 == n_it;
       if (time_kernels) cudaEventRecord(tev[h].ev[3 * i], d->stream);
-      d->launch_cn();
+      if (fused && i == 0) d->launch_cn_refill();
+      else d->launch_cn();
       if (time_kernels) cudaEventRecord(tev[h].ev[3 * i + 1], d->stream);
       d->launch_vn(last);
       if (time_kernels) cudaEventRecord(tev[h].ev[3 * i + 2], d->stream);
@@ -980,6 +1016,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     if (time_kernels) timed_iters[h] = n_it;
     rep.cn_launches += n_it;
     rep.vn_launches += n_it;
+    rep.cn_refill_launches += fused ? 1 : 0;
     if (time_kernels) cudaEventRecord(sev[h].ev[0], d->stream);
     d->launch_check();
     rep.other_launches++;
@@ -1010,7 +1047,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     }
     if (time_kernels) cudaEventRecord(sev[h].ev[2], d->stream);
     CU_TRY(record(d->ev_extracted[h]));
-    d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed);
+    d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed, !fused);
     CU_TRY(record(d->ev_refilled));
     if (time_kernels) cudaEventRecord(sev[h].ev[3], d->stream);
     CU_TRY(cudaMemcpyAsync(d->h_summary.p + h, d->d_summary.p, sizeof(dev::SchedSummary), cudaMemcpyDeviceToHost,
@@ -1102,6 +1139,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       rep.graph_launches++;
       rep.cn_launches += k_check;
       rep.vn_launches += k_check;
+      rep.cn_refill_launches += fused ? 1 : 0;
       rep.other_launches += 5 + sc.early_retire;
       rep.n_checks_run++;
     } else {
@@ -1122,6 +1160,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   // the run-ahead period was enqueued but did no work
   rep.cn_launches -= k_check;
   rep.vn_launches -= k_check;
+  rep.cn_refill_launches -= fused ? 1 : 0;
   rep.other_launches -= 1;
   rep.n_checks_run -= 1;
 

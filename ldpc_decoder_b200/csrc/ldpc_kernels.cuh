@@ -30,6 +30,9 @@ namespace dev {
 #ifndef LDPC_THREADS
 #define LDPC_THREADS 256
 #endif
+#ifndef LDPC_HMIN_CLAMP
+#define LDPC_HMIN_CLAMP 1 // fp16 table index: packed-half clamp + byte offsets (A/B on B200: CN +2.4 %, VN +5.1 %)
+#endif
 constexpr int kThreads = LDPC_THREADS; // CTA size of the streaming kernels
 // Rows of degree <= D are held in registers (one read, one write per message); D is a template parameter chosen
 // per code from {4, 6, 8} (host: pick_reg_degree).  Fewer registers buy a resident CTA: measured on B200
@@ -44,13 +47,38 @@ constexpr int cn_threads_for(int D) { return D <= 6 ? 512 : kThreads; }
 constexpr int kPhiTableSize = 32768; // fp16 phi_abs table entries (all non-negative half bit patterns)
 
 // ---------------------------------------------------------------- memory helpers
+// Cache policy of the streaming accesses (A/B-tested on B200 with scripts/ab_kernels.py; the defaults are what won):
+//   LDPC_LD_MODE 0 = ld.global.cs (evict-first), 1 = ld.global (default), 2 = ld.global.cg, 3 = ld.global.nc.L1::no_allocate
+//   LDPC_ST_MODE 0 = st.global.cs,               1 = st.global (write-back), 2 = st.global.cg
+#ifndef LDPC_LD_MODE
+#define LDPC_LD_MODE 0
+#endif
+#ifndef LDPC_ST_MODE
+#define LDPC_ST_MODE 0
+#endif
+#if LDPC_LD_MODE == 0
+#define LDPC_LD_OP "ld.global.cs.v4.u32"
+#elif LDPC_LD_MODE == 1
+#define LDPC_LD_OP "ld.global.v4.u32"
+#elif LDPC_LD_MODE == 2
+#define LDPC_LD_OP "ld.global.cg.v4.u32"
+#else
+#define LDPC_LD_OP "ld.global.nc.L1::no_allocate.v4.u32"
+#endif
+#if LDPC_ST_MODE == 0
+#define LDPC_ST_OP "st.global.cs.v4.u32"
+#elif LDPC_ST_MODE == 1
+#define LDPC_ST_OP "st.global.v4.u32"
+#else
+#define LDPC_ST_OP "st.global.cg.v4.u32"
+#endif
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) { // read once: evict-first
   uint4 r;
-  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile(LDPC_LD_OP " {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
-  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  asm volatile(LDPC_ST_OP " [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint4 ld_cached(const uint4 *p) { // re-read soon (large-degree rows): keep in L1/L2
   uint4 r;
@@ -111,8 +139,14 @@ struct TraitsF32 {
   __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *, uint32_t) {
     return __float_as_uint(phi_abs_f32(__uint_as_float(w)));
   }
+  // magnitude r (any sign bit) with the sign of s
+  __device__ static __forceinline__ uint32_t with_sign(uint32_t r, uint32_t s) {
+    return (r & ~kSignMask) | (s & kSignMask);
+  }
   // sign word with bit set where the frame's bit is 1 (bits = low kFramesPerWord bits)
   __device__ static __forceinline__ uint32_t sign_from_bits(uint32_t bits) { return bits << 31; }
+  // all-ones in the lanes of the word whose frame bit is set
+  __device__ static __forceinline__ uint32_t lane_mask(uint32_t bits) { return 0u - (bits & 1u); }
   // hard decision bits of a posterior word: bit=1 <=> sign bit clear (flood.cu:180)
   __device__ static __forceinline__ uint32_t hard_bits(uint32_t w) { return (~w) >> 31; }
   // channel value -> llr (flood.cu:58, :73)
@@ -133,21 +167,39 @@ struct TraitsF16 {
 
   __device__ static __forceinline__ __half2 h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
   __device__ static __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
-  __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFF7FFFu; }
+  __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return u32(__habs2(h2(w))); } // clears both sign bits
   // one IEEE half rounding per add/sub, as the reference's scalar __half arithmetic (flood.cu:95-99, 134-147)
   __device__ static __forceinline__ uint32_t add_w(uint32_t a, uint32_t b) { return u32(__hadd2_rn(h2(a), h2(b))); }
   __device__ static __forceinline__ uint32_t sub_w(uint32_t a, uint32_t b) { return u32(__hsub2_rn(h2(a), h2(b))); }
   // `last` = index from which every table entry is zero (2e^-x underflows in half above x ~ 17.3): only
-  // [0, last] is staged in shared memory, larger indices clamp to it
+  // [0, last] is staged in shared memory, larger indices clamp to it.
+  // The argument is never negative: the check-node pass looks up S - |m_e| with S = the round-to-nearest sum of all
+  // |m_e| (monotone rounding: S >= every term), the variable-node pass |T - m_e|.  Non-negative halves order like their
+  // bit patterns, so the clamp is one packed half min (a NaN, which only a NaN input can produce, clamps to `last`);
+  // doubling both indices at once (2*last < 2^16: no carry) gives the two byte offsets into the table.
   __device__ static __forceinline__ uint32_t phi_abs_w(uint32_t w, const uint16_t *tab, uint32_t last) {
-    // negative / NaN preimages clamp to the table's first entry (flood.cu:10, 26)
+#if LDPC_HMIN_CLAMP
+    const uint32_t c = u32(__hmin2(h2(w), h2(last * 0x10001u)));
+    const uint32_t c2 = c + c;
+    const uint8_t *tb = reinterpret_cast<const uint8_t *>(tab);
+    const uint32_t lo = *reinterpret_cast<const uint16_t *>(tb + (c2 & 0xFFFFu));
+    const uint32_t hi = *reinterpret_cast<const uint16_t *>(tb + (c2 >> 16));
+    return __byte_perm(lo, hi, 0x5410);
+#else
+    // first version: negative / NaN preimages clamp to the table's first entry (flood.cu:10, 26)
     const uint32_t c = u32(__hmax2(h2(w), h2(0u)));
     const uint32_t lo = tab[min(c & 0x7FFFu, last)];
     const uint32_t hi = tab[min(c >> 16, last)];
+#endif
     return lo | (hi << 16);
   }
+  // table entries are non-negative halves: nothing to clear in r
+  __device__ static __forceinline__ uint32_t with_sign(uint32_t r, uint32_t s) { return r | (s & kSignMask); }
   __device__ static __forceinline__ uint32_t sign_from_bits(uint32_t bits) {
     return ((bits & 1u) << 15) | ((bits & 2u) << 30);
+  }
+  __device__ static __forceinline__ uint32_t lane_mask(uint32_t bits) {
+    return ((bits & 1u) | ((bits & 2u) << 15)) * 0xFFFFu;
   }
   __device__ static __forceinline__ uint32_t hard_bits(uint32_t w) {
     const uint32_t n = ~w;
@@ -216,12 +268,37 @@ template <class Tr> __device__ __forceinline__ uint32_t load_frame_bits(const ui
 // sign = sign(m_e) xor parity, parity = syndrome bit xor (number of non-negative inputs) (flood.cu:77-115).
 // The row offsets and syndrome bits of the thread's NEXT item are fetched while the current row's messages are
 // in flight, so the dependent index -> message load chain is off the critical path.
-template <class Tr, int kMaxRegDeg>
-__global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMaxRegDeg) * kThreads / cn_threads_for(kMaxRegDeg))
-    cn_update_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
-                     const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
-                     const uint32_t *__restrict__ done) {
+//
+// kRefill (cn_update_refill_kernel, the first check-node pass after a refill): the refill kernel has only written the
+// new frames' PRIORS; the messages a new frame starts from, phi(prior of the edge's variable) (flood.cu:297-323), are
+// produced here, in the pass that reads and rewrites every message row anyway -- a gather of the prior vector per edge
+// for the vectors that hold new slots instead of a separate read-modify-write of those message vectors.
+struct CnRefillArgs {
+  const uint4 *llr0;         // priors [N][P]
+  const uint32_t *edge_var;  // variable of each check-major edge
+  const uint8_t *new_mask;   // bit per slot: refilled since the last check-node pass
+};
+
+// message vector a new-frame lane starts from: phi_abs(|prior|) with the prior's sign
+template <class Tr>
+__device__ __forceinline__ uint4 start_message(const uint4 &prior, const uint16_t *tab, uint32_t tab_last) {
+  uint4 o;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const uint32_t pw = word(prior, w);
+    const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pw), tab, tab_last);
+    word(o, w) = Tr::with_sign(r, pw);
+  }
+  return o;
+}
+
+template <class Tr, int kMaxRegDeg, bool kRefill, class Idx>
+__device__ __forceinline__ void
+cn_update_body(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
+               const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
+               const uint32_t *__restrict__ done, const CnRefillArgs ra) {
   if (done && *done) return; // the device-side scheduler has retired every frame: run-ahead launches are no-ops
+  constexpr uint32_t kFull = (1u << Tr::kFramesPerVec) - 1u;
   const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
   const uint32_t G = 1u << log2_g; // row stride in vectors
   // active vectors per row: the scheduler may have compacted the live frames into the low slots (early retire)
@@ -247,7 +324,7 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
       sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
     }
     const uint32_t a = a_next, deg = b_next - a_next, sbits = sbits_next;
-    uint4 *p = msg + (size_t(a) << log2_g) + g;
+    uint4 *p = msg + ((Idx(a) << log2_g) + g);
     // parity seed: syndrome bit xor (deg & 1); xor-ing the raw sign bits of all inputs then gives
     // syndrome ^ #(non-negative inputs)
     const uint32_t odd = (deg & 1u) ? Tr::kSignMask : 0u;
@@ -255,11 +332,32 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
 #pragma unroll
     for (int w = 0; w < 4; ++w)
       word(X, w) = Tr::sign_from_bits(sbits >> (w * Tr::kFramesPerWord)) ^ odd;
+    // slots of this vector refilled since the last pass, and their lanes
+    uint32_t nm = 0;
+    uint4 SEL = make_uint4(0, 0, 0, 0);
+    if (kRefill) {
+      nm = load_frame_bits<Tr>(ra.new_mask, g);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) word(SEL, w) = Tr::lane_mask(nm >> (w * Tr::kFramesPerWord));
+    }
     if (deg <= kMaxRegDeg) {
       uint4 m[kMaxRegDeg];
 #pragma unroll
       for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg) m[k] = ld_stream(p + (size_t(k) << log2_g));
+        if (k < deg) m[k] = (kRefill && nm == kFull) ? make_uint4(0, 0, 0, 0) : ld_stream(p + (Idx(k) << log2_g));
+      if (kRefill && nm) {
+        uint4 pr[kMaxRegDeg];
+#pragma unroll
+        for (int k = 0; k < kMaxRegDeg; ++k)
+          if (k < deg) pr[k] = ld_stream(ra.llr0 + ((Idx(__ldg(ra.edge_var + a + k)) << log2_g) + g));
+#pragma unroll
+        for (int k = 0; k < kMaxRegDeg; ++k)
+          if (k < deg) {
+            const uint4 o = start_message<Tr>(pr[k], tab, tab_last);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) word(m[k], w) = (word(m[k], w) & ~word(SEL, w)) | (word(o, w) & word(SEL, w));
+          }
+      }
       if (Tr::kPrefetchCN && item + stride < total) { // next item's indices behind the message loads
         const uint32_t c = uint32_t((item + stride) >> log2_ga);
         a_next = __ldg(row_ptr + c);
@@ -283,9 +381,9 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
           for (int w = 0; w < 4; ++w) {
             const uint32_t mw = word(m[k], w);
             const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-            word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+            word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
           }
-          st_stream(p + (size_t(k) << log2_g), o);
+          st_stream(p + (Idx(k) << log2_g), o);
         }
     } else {
       if (Tr::kPrefetchCN && item + stride < total) {
@@ -294,8 +392,19 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
         b_next = __ldg(row_ptr + c + 1);
         sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
       }
+      // long rows: two passes; a refilled lane's start message is recomputed from the prior in both
+      auto load_row = [&](uint32_t k) {
+        uint4 mk = ld_cached(p + (Idx(k) << log2_g));
+        if (kRefill && nm) {
+          const uint4 o =
+              start_message<Tr>(ld_cached(ra.llr0 + ((Idx(__ldg(ra.edge_var + a + k)) << log2_g) + g)), tab, tab_last);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) word(mk, w) = (word(mk, w) & ~word(SEL, w)) | (word(o, w) & word(SEL, w));
+        }
+        return mk;
+      };
       for (uint32_t k = 0; k < deg; ++k) {
-        uint4 mk = ld_cached(p + (size_t(k) << log2_g));
+        uint4 mk = load_row(k);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           word(S, w) = Tr::add_w(word(S, w), Tr::abs_w(word(mk, w)));
@@ -303,18 +412,38 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
         }
       }
       for (uint32_t k = 0; k < deg; ++k) {
-        uint4 mk = ld_cached(p + (size_t(k) << log2_g));
+        uint4 mk = load_row(k);
         uint4 o;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           const uint32_t mw = word(mk, w);
           const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-          word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+          word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
         }
-        st_stream(p + (size_t(k) << log2_g), o);
+        st_stream(p + (Idx(k) << log2_g), o);
       }
     }
   }
+}
+
+// Idx = uint32_t when every vector index (E * vectors per row) fits 32 bits: one IMAD.WIDE per address instead of a
+// 64-bit shift/add chain (the host picks; size_t otherwise, e.g. 2^13 slots of a 4M-bit code)
+template <class Tr, int kMaxRegDeg, class Idx>
+__global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMaxRegDeg) * kThreads / cn_threads_for(kMaxRegDeg))
+    cn_update_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
+                     const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
+                     const uint32_t *__restrict__ done) {
+  cn_update_body<Tr, kMaxRegDeg, false, Idx>(msg, row_ptr, syn, phi_table, tab_last, n_checks, log2_g, done, CnRefillArgs{});
+}
+
+// first check-node pass after a refill (one launch per check period): message and prior vectors of a row are both in
+// registers, so it runs 2 CTAs/SM with twice the loads in flight per thread
+template <class Tr, int kMaxRegDeg>
+__global__ void __launch_bounds__(kThreads, 2)
+    cn_update_refill_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr,
+                            const uint8_t *__restrict__ syn, const uint16_t *__restrict__ phi_table, uint32_t tab_last,
+                            uint32_t n_checks, uint32_t log2_g, const uint32_t *__restrict__ done, const CnRefillArgs ra) {
+  cn_update_body<Tr, kMaxRegDeg, true, size_t>(msg, row_ptr, syn, phi_table, tab_last, n_checks, log2_g, done, ra);
 }
 
 // ---------------------------------------------------------------- check-node pass, long rows (high-rate codes)
@@ -389,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 3)
         for (int w = 0; w < 4; ++w) {
           const uint32_t mw = word(m[k], w);
           const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-          word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+          word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
         }
         st_stream(p + (size_t(k) << log2_g), o);
       }
@@ -511,7 +640,7 @@ __global__ void __launch_bounds__(kBulkTileVec, 2)
         for (int w = 0; w < 4; ++w) {
           const uint32_t mw = word(m[k], w);
           const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-          word(o, w) = (r & ~Tr::kSignMask) | ((mw ^ word(X, w)) & Tr::kSignMask);
+          word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
         }
         tile[size_t(k) * kBulkTileVec + tid] = o;
       }
@@ -534,7 +663,7 @@ __global__ void __launch_bounds__(kBulkTileVec, 2)
 // One thread = (variable v, frame vector g).  T = llr0 + sum of incoming c2v in CSC order; every edge gets
 // phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).
 // The gather list of the thread's NEXT item is fetched while the current messages are in flight.
-template <class Tr, bool kFinalBits, int kMaxRegDeg>
+template <class Tr, bool kFinalBits, int kMaxRegDeg, class Idx>
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
     vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ col_ptr,
                      const uint32_t *__restrict__ in_to_out, uint8_t *__restrict__ hard,
@@ -570,14 +699,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
         if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
     }
     const uint32_t a = a_next, deg = deg_next;
-    uint4 T = ld_stream(llr0 + (size_t(v) << log2_g) + g);
+    uint4 T = ld_stream(llr0 + ((Idx(v) << log2_g) + g));
     if (deg <= kMaxRegDeg) {
       uint4 m[kMaxRegDeg];
       uint32_t rows[kMaxRegDeg];
 #pragma unroll
       for (int k = 0; k < kMaxRegDeg; ++k) {
         rows[k] = rows_next[k];
-        if (k < deg) m[k] = ld_stream(msg + (size_t(rows[k]) << log2_g) + g);
+        if (k < deg) m[k] = ld_stream(msg + ((Idx(rows[k]) << log2_g) + g));
       }
       if (Tr::kPrefetchVN && item + stride < total) { // next item's gather list behind the message loads
         const uint32_t vn = uint32_t((item + stride) >> log2_ga);
@@ -601,9 +730,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
           for (int w = 0; w < 4; ++w) {
             const uint32_t pre = Tr::sub_w(word(T, w), word(m[k], w));
             const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
-            word(o, w) = (r & ~Tr::kSignMask) | (pre & Tr::kSignMask);
+            word(o, w) = Tr::with_sign(r, pre);
           }
-          st_stream(msg + (size_t(rows[k]) << log2_g) + g, o);
+          st_stream(msg + ((Idx(rows[k]) << log2_g) + g), o);
         }
     } else {
       if (Tr::kPrefetchVN && item + stride < total) {
@@ -615,19 +744,19 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
           if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
       }
       for (uint32_t k = 0; k < deg; ++k) {
-        const uint4 mk = ld_cached(msg + (size_t(__ldg(in_to_out + a + k)) << log2_g) + g);
+        const uint4 mk = ld_cached(msg + ((Idx(__ldg(in_to_out + a + k)) << log2_g) + g));
 #pragma unroll
         for (int w = 0; w < 4; ++w) word(T, w) = Tr::add_w(word(T, w), word(mk, w));
       }
       for (uint32_t k = 0; k < deg; ++k) {
-        uint4 *pk = msg + (size_t(__ldg(in_to_out + a + k)) << log2_g) + g;
+        uint4 *pk = msg + ((Idx(__ldg(in_to_out + a + k)) << log2_g) + g);
         const uint4 mk = ld_cached(pk);
         uint4 o;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           const uint32_t pre = Tr::sub_w(word(T, w), word(mk, w));
           const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
-          word(o, w) = (r & ~Tr::kSignMask) | (pre & Tr::kSignMask);
+          word(o, w) = Tr::with_sign(r, pre);
         }
         st_stream(pk, o);
       }
@@ -682,12 +811,16 @@ struct RefillEntry {     // one new frame
   uint32_t pad;
 };
 
-// One thread = (variable i, 16-byte slot vector g).  New frames land in scattered slots, so a 2- or 4-byte store
-// per (row, slot) would cost a 32-byte sector read-modify-write each.  Instead every vector that contains at least
-// one new slot is rewritten whole: read 16 B, replace the new lanes, write 16 B -- for the prior row and for
-// every edge row of the variable.  prior = llr(channel value) (0 for punctured variables), edges get phi(prior)
-// (flood.cu:47-75, 297-323).  Vectors without new slots are skipped; a vector of only new slots is not read.
-template <class Tr, bool kPacked>
+// One thread = (16-byte slot vector g, every variable i of its stride).  New frames land in scattered slots, so a 2- or
+// 4-byte store per (row, slot) would cost a 32-byte sector read-modify-write each.  Instead every vector that contains
+// at least one new slot is rewritten whole: read 16 B, replace the new lanes, write 16 B -- for the prior row and, with
+// kMsgRows, for every edge row of the variable.  prior = llr(channel value) (0 for punctured variables), edges get
+// phi(prior) (flood.cu:47-75, 297-323).  Vectors without new slots are skipped; a vector of only new slots is not read.
+// The grid stride is a multiple of the row length (host: grid_misc), so a thread keeps its vector g: the source
+// addresses of its new lanes are looked up once, not once per variable.
+// kMsgRows = false (decode(), fused path): only the priors are written here; the first check-node pass of the period
+// (cn_update_refill_kernel) derives the start messages from them.
+template <class Tr, bool kPacked, bool kMsgRows>
 __global__ void __launch_bounds__(kThreads)
     refill_kernel(uint4 *__restrict__ msg, uint4 *__restrict__ llr0, const void *__restrict__ src,
                   const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
@@ -701,42 +834,45 @@ __global__ void __launch_bounds__(kThreads)
   constexpr uint32_t kFull = (1u << V) - 1u;
   const uint32_t G = 1u << log2_g;
   const uint64_t total = uint64_t(n_vars) << log2_g;
-  for (uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; item < total;
-       item += uint64_t(gridDim.x) * blockDim.x) {
-    const uint32_t i = uint32_t(item >> log2_g);
-    const uint32_t g = uint32_t(item) & (G - 1u);
-    const uint32_t nm = load_frame_bits<Tr>(reinterpret_cast<const uint8_t *>(new_mask), g);
-    if (nm == 0) continue;
-    uint4 L = make_uint4(0, 0, 0, 0), O = make_uint4(0, 0, 0, 0), SEL = make_uint4(0, 0, 0, 0);
+  const uint64_t first = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t g = uint32_t(first) & (G - 1u);
+  const uint32_t nm = load_frame_bits<Tr>(reinterpret_cast<const uint8_t *>(new_mask), g);
+  if (nm == 0) return; // this thread's vector holds no new frame
+  uint64_t off[V];     // element offset of each new lane's first channel value
+  uint64_t src_stride = 0;
+  uint4 SEL;
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      if ((nm >> j) & 1u) {
-        const RefillEntry en = entries[__ldg(slot_entry + g * V + j)];
-        const uint64_t at = en.src_offset + uint64_t(i) * en.src_stride;
-        // packed hard-decision input (1 bit per transmitted variable, frame-major words): bit 1 <-> +1
-        uint32_t pbit = 0;
-        if (packed_bits && i < n_regular)
-          pbit = (__ldg(static_cast<const uint32_t *>(src) + en.src_offset + (i >> 5)) >> (i & 31u)) & 1u;
-        if (V == 4) {
-          uint32_t raw = 0;
-          if (i < n_regular)
-            raw = TraitsF32::to_llr(packed_bits ? (pbit ? 0x3F800000u : 0xBF800000u)
-                                                : __ldg(static_cast<const uint32_t *>(src) + at), channel, param);
-          const uint32_t r = __float_as_uint(phi_abs_f32(__uint_as_float(raw & 0x7FFFFFFFu)));
-          word(L, j & 3) = raw;
-          word(O, j & 3) = (r & 0x7FFFFFFFu) | (raw & 0x80000000u);
-          word(SEL, j & 3) = 0xFFFFFFFFu;
-        } else {
-          uint32_t raw = 0;
-          if (i < n_regular)
-            raw = TraitsF16::to_llr(packed_bits ? uint16_t(pbit ? 0x3C00u : 0xBC00u)
-                                                : __ldg(static_cast<const uint16_t *>(src) + at), channel, param);
-          const uint32_t r = __ldg(phi_table + (raw & 0x7FFFu));
-          const uint32_t o = (r & 0x7FFFu) | (raw & 0x8000u);
-          const int sh = (j & 1) * 16;
-          word(L, (j >> 1) & 3) |= raw << sh;
-          word(O, (j >> 1) & 3) |= o << sh;
-          word(SEL, (j >> 1) & 3) |= 0xFFFFu << sh;
+  for (int j = 0; j < V; ++j) {
+    off[j] = 0;
+    if ((nm >> j) & 1u) {
+      const RefillEntry en = entries[__ldg(slot_entry + g * V + j)];
+      off[j] = en.src_offset;
+      src_stride = en.src_stride; // the same for every frame of a launch
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 4; ++w) word(SEL, w) = Tr::lane_mask(nm >> (w * Tr::kFramesPerWord));
+  for (uint64_t item = first; item < total; item += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t i = uint32_t(item >> log2_g);
+    uint4 L = make_uint4(0, 0, 0, 0), O = make_uint4(0, 0, 0, 0);
+    if (i < n_regular) {
+      const uint64_t at_i = uint64_t(i) * src_stride;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        if ((nm >> j) & 1u) {
+          // packed hard-decision input (1 bit per transmitted variable, frame-major words): bit 1 <-> +1
+          uint32_t pbit = 0;
+          if (packed_bits) pbit = (__ldg(static_cast<const uint32_t *>(src) + off[j] + (i >> 5)) >> (i & 31u)) & 1u;
+          if (V == 4) {
+            word(L, j & 3) = TraitsF32::to_llr(packed_bits ? (pbit ? 0x3F800000u : 0xBF800000u)
+                                                           : __ldg(static_cast<const uint32_t *>(src) + off[j] + at_i),
+                                               channel, param);
+          } else {
+            const uint32_t raw = TraitsF16::to_llr(packed_bits ? uint16_t(pbit ? 0x3C00u : 0xBC00u)
+                                                               : __ldg(static_cast<const uint16_t *>(src) + off[j] + at_i),
+                                                   channel, param);
+            word(L, (j >> 1) & 3) |= raw << ((j & 1) * 16);
+          }
         }
       }
     }
@@ -748,14 +884,25 @@ __global__ void __launch_bounds__(kThreads)
       for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(L, w);
       st_stream(p, old);
     }
-    const uint32_t a = __ldg(col_ptr + i), b = __ldg(col_ptr + i + 1);
-    for (uint32_t ie = a; ie < b; ++ie) {
-      uint4 *p = msg + (size_t(__ldg(in_to_out + ie)) << log2_g) + g;
-      uint4 old = make_uint4(0, 0, 0, 0);
-      if (nm != kFull) old = ld_stream(p);
+    if (kMsgRows) {
+      // start messages: phi_abs(|prior|) with the prior's sign (punctured variables: phi_abs(0))
 #pragma unroll
-      for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(O, w);
-      st_stream(p, old);
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t lw = word(L, w);
+        uint32_t r;
+        if (V == 4) r = __float_as_uint(phi_abs_f32(__uint_as_float(lw & 0x7FFFFFFFu)));
+        else r = uint32_t(__ldg(phi_table + (lw & 0x7FFFu))) | (uint32_t(__ldg(phi_table + ((lw >> 16) & 0x7FFFu))) << 16);
+        word(O, w) = ((r & ~Tr::kSignMask) | (lw & Tr::kSignMask)) & word(SEL, w);
+      }
+      const uint32_t a = __ldg(col_ptr + i), b = __ldg(col_ptr + i + 1);
+      for (uint32_t ie = a; ie < b; ++ie) {
+        uint4 *p = msg + (size_t(__ldg(in_to_out + ie)) << log2_g) + g;
+        uint4 old = make_uint4(0, 0, 0, 0);
+        if (nm != kFull) old = ld_stream(p);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(O, w);
+        st_stream(p, old);
+      }
     }
   }
 }

@@ -649,3 +649,56 @@ def test_bulk_async_check_node_kernel_is_bit_exact(prec, monkeypatch):
     assert np.array_equal(it_a, it_b)
     conv = it_a < 40
     assert np.array_equal(res_a[conv], res_b[conv])
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+@pytest.mark.parametrize("name,channel,noise,n_frames,log2p", [
+    ("readme13", "awgn", 0.6, 300, 6),   # punctured tail, degrees <= 6: register path of the fused pass
+    ("readme13", "bsc", 0.03, 100, 5),
+    ("reg36", "awgn", 0.78, 50, 6),      # fewer frames than slots: unused slots are never "new"
+    ("tiny", "awgn", 0.7, 200, 5),
+])
+def test_fused_refill_equals_stand_alone_refill(small_codes, prec, name, channel, noise, n_frames, log2p, monkeypatch):
+    """EXPERIMENT LDPC_B200_FUSED_REFILL=1: decode() writes only the priors of new frames and lets the first check-node
+    pass of the period build their start messages (cn_update_refill_kernel).  The default is the stand-alone refill
+    that writes the message rows itself (the reference's flood_refill, flood.cu:297-323): results, iteration counts
+    and the message state after a decode must be identical bit for bit, in both precisions."""
+    gen, path = small_codes[name]
+    fp16 = prec == "fp16"
+    inp, syn, bits, prm = _frames(gen, n_frames, channel, noise, 5, np.float16 if fp16 else np.float32)
+    ch = L.AWGN if channel == "awgn" else L.BSC
+    monkeypatch.setenv("LDPC_B200_FUSED_REFILL", "1")
+    a = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, log2p)
+    monkeypatch.delenv("LDPC_B200_FUSED_REFILL")
+    b = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, log2p)
+    ra, ia, repa = a.decode(ch, prm, inp, syn, num_iter_max=50, num_iter_check_parity=5)
+    rb_, ib, repb = b.decode(ch, prm, inp, syn, num_iter_max=50, num_iter_check_parity=5)
+    assert repa["cn_refill_launches"] > 0 and repb["cn_refill_launches"] == 0
+    assert repa["cn_launches"] == repb["cn_launches"] and repa["global_iters"] == repb["global_iters"]
+    assert np.array_equal(ia, ib) and np.array_equal(ra, rb_)
+    P = a.parallel_factor()
+    for s in sorted({0, 1, min(n_frames, P) - 1, P - 1}):
+        if s < min(n_frames, P):
+            assert np.array_equal(a.messages(s).view(np.uint32), b.messages(s).view(np.uint32)), s
+    # timed path (plain launches) accounts the fused pass apart from the plain ones
+    _, it, rept = a.decode(ch, prm, inp, syn, num_iter_max=50, num_iter_check_parity=5, flags=L.FLAG_TIME_KERNELS)
+    assert np.array_equal(it, ia) and rept["cn_refill_s"] > 0 and rept["cn_refill_launches"] == repa["cn_refill_launches"]
+
+
+def test_fused_refill_long_rows(monkeypatch):
+    """Fused refill on check rows longer than the register-resident degree (the two-pass path of the check-node pass)."""
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_regular_code(1 << 12, 3, 12, seed=3)  # degree-12 rows: re-read path, no row splitting
+    code = L.Code.from_generated(gen)
+    for prec, dt in ((L.FP16, np.float16), (L.FP32, np.float32)):
+        inp, syn, bits, prm = _frames(gen, 150, "bsc", 0.01, 9, dt)
+        monkeypatch.setenv("LDPC_B200_FUSED_REFILL", "1")
+        a = L.Decoder(code, prec, 5)
+        monkeypatch.delenv("LDPC_B200_FUSED_REFILL")
+        b = L.Decoder(code, prec, 5)
+        ra, ia, repa = a.decode(L.BSC, prm, inp, syn, num_iter_max=30, num_iter_check_parity=3)
+        rb_, ib, _ = b.decode(L.BSC, prm, inp, syn, num_iter_max=30, num_iter_check_parity=3)
+        assert repa["cn_refill_launches"] > 0
+        assert np.array_equal(ia, ib) and np.array_equal(ra, rb_)
+        assert harness.count_bit_errors(ra, bits)[ia < 30].sum() == 0
