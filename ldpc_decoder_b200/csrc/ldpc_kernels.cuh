@@ -264,6 +264,34 @@ template <class Tr> __device__ __forceinline__ uint32_t load_frame_bits(const ui
   return (row_bytes[g >> 1] >> ((g & 1u) * 4u)) & 0xFu;
 }
 
+// ---------------------------------------------------------------- output vectors of the two passes
+// check node:    o = phi_abs(S - |m|) with sign(m) xor parity          (flood.cu:100-113)
+// variable node: o = phi_abs(|T - m|) with the sign of T - m           (flood.cu:141-155)
+template <class Tr>
+__device__ __forceinline__ uint4 cn_out_vec(const uint4 &S, const uint4 &m, const uint4 &X, const uint16_t *tab,
+                                            uint32_t tab_last) {
+  uint4 o;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const uint32_t mw = word(m, w);
+    const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
+    word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
+  }
+  return o;
+}
+
+template <class Tr>
+__device__ __forceinline__ uint4 vn_out_vec(const uint4 &T, const uint4 &m, const uint16_t *tab, uint32_t tab_last) {
+  uint4 o;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const uint32_t pre = Tr::sub_w(word(T, w), word(m, w));
+    const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
+    word(o, w) = Tr::with_sign(r, pre);
+  }
+  return o;
+}
+
 // ---------------------------------------------------------------- degree dispatch
 // A row of degree <= kMaxRegDeg is processed by code specialised on its exact degree (no per-edge `k < deg` branch):
 // run<D>(deg, f) calls f(std::integral_constant<int, deg>) for deg in [1, D].  All threads of a warp share the row,
@@ -390,13 +418,7 @@ cn_update_body(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, co
         }
 #pragma unroll
         for (int k = 0; k < DEG; ++k) {
-          uint4 o;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const uint32_t mw = word(m[k], w);
-            const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-            word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
-          }
+          const uint4 o = cn_out_vec<Tr>(S, m[k], X, tab, tab_last);
           st_stream(p + (Idx(k) << log2_g), o);
         }
       });
@@ -428,13 +450,7 @@ cn_update_body(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, co
       }
       for (uint32_t k = 0; k < deg; ++k) {
         uint4 mk = load_row(k);
-        uint4 o;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t mw = word(mk, w);
-          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-          word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
-        }
+        const uint4 o = cn_out_vec<Tr>(S, mk, X, tab, tab_last);
         st_stream(p + (Idx(k) << log2_g), o);
       }
     }
@@ -528,13 +544,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 #pragma unroll
     for (int k = 0; k < kChunk; ++k)
       if (k0 + k < deg) {
-        uint4 o;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t mw = word(m[k], w);
-          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-          word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
-        }
+        const uint4 o = cn_out_vec<Tr>(S, m[k], X, tab, tab_last);
         st_stream(p + (size_t(k) << log2_g), o);
       }
   }
@@ -650,13 +660,7 @@ __global__ void __launch_bounds__(kBulkTileVec, 2)
 #pragma unroll
     for (int k = 0; k < kMaxRegDeg; ++k)
       if (k < deg) {
-        uint4 o;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t mw = word(m[k], w);
-          const uint32_t r = Tr::phi_abs_w(Tr::sub_w(word(S, w), Tr::abs_w(mw)), tab, tab_last);
-          word(o, w) = Tr::with_sign(r, mw ^ word(X, w));
-        }
+        const uint4 o = cn_out_vec<Tr>(S, m[k], X, tab, tab_last);
         tile[size_t(k) * kBulkTileVec + tid] = o;
       }
     bulk::fence_async_smem(); // generic-proxy writes -> visible to the bulk-copy (async) proxy
@@ -748,13 +752,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
         }
 #pragma unroll
         for (int k = 0; k < DEG; ++k) {
-          uint4 o;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const uint32_t pre = Tr::sub_w(word(T, w), word(m[k], w));
-            const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
-            word(o, w) = Tr::with_sign(r, pre);
-          }
+          const uint4 o = vn_out_vec<Tr>(T, m[k], tab, tab_last);
           st_stream(msg + at[k], o);
         }
       });
@@ -775,13 +773,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
       for (uint32_t k = 0; k < deg; ++k) {
         uint4 *pk = msg + ((Idx(__ldg(in_to_out + a + k)) << log2_g) + g);
         const uint4 mk = ld_cached(pk);
-        uint4 o;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t pre = Tr::sub_w(word(T, w), word(mk, w));
-          const uint32_t r = Tr::phi_abs_w(Tr::abs_w(pre), tab, tab_last);
-          word(o, w) = Tr::with_sign(r, pre);
-        }
+        const uint4 o = vn_out_vec<Tr>(T, mk, tab, tab_last);
         st_stream(pk, o);
       }
     }
