@@ -280,7 +280,7 @@ struct ldpc_b200_decoder {
   vn_fn k_vn = nullptr, k_vnb = nullptr;
   int deg_cn = 8, deg_vn = 8;
   int cn_parts = 1; // > 1: check rows are split over this many lanes
-  int threads_cn = dev::kThreads;
+  int threads_cn = dev::kThreads, threads_vn = dev::kThreads;
   bool cn_bulk = false;   // experiment (LDPC_B200_CN_BULK=1): bulk-async staged check-node kernel
   size_t smem_cn = 0;     // dynamic shared memory of the check-node kernel
   void launch_cn() {
@@ -297,7 +297,7 @@ struct ldpc_b200_decoder {
         tab_last, M, log2G, done_flag(), ra);
   }
   void launch_vn(bool bits) {
-    (bits ? k_vnb : k_vn)<<<bits ? grid_vnb : grid_vn, dev::kThreads, smem_tab, stream>>>(
+    (bits ? k_vnb : k_vn)<<<bits ? grid_vnb : grid_vn, threads_vn, smem_tab, stream>>>(
         reinterpret_cast<uint4 *>(d_msg.p), reinterpret_cast<const uint4 *>(d_llr0.p), d_col_ptr.p, d_in_to_out.p,
         reinterpret_cast<uint8_t *>(d_hard.p), d_phi_table.p, tab_last, N, log2G, done_flag());
   }
@@ -494,6 +494,7 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   unsigned local_world = 1;
   if (const char *lw = std::getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(lw));
   d->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency() / local_world));
+  if (const char *ht = std::getenv("LDPC_B200_HOST_THREADS")) d->host_threads = std::max(1, atoi(ht)); // feed experiments
   d->precision = cfg->precision;
   d->elem = cfg->precision == LDPC_B200_FP32 ? 4 : 2;
   d->M = uint32_t(code.n_outputs());
@@ -616,8 +617,9 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   }
   d->grid_cn = occupancy_grid(d->k_cn, d->threads_cn, d->smem_cn, d->n_sms, cn_items);
   if (d->k_cn_refill) d->grid_cn_refill = occupancy_grid(d->k_cn_refill, dev::kThreads, d->smem_tab, d->n_sms, cn_items);
-  d->grid_vn = occupancy_grid(d->k_vn, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
-  d->grid_vnb = occupancy_grid(d->k_vnb, dev::kThreads, d->smem_tab, d->n_sms, vn_items);
+  d->threads_vn = dev::vn_threads_for(d->deg_vn);
+  d->grid_vn = occupancy_grid(d->k_vn, d->threads_vn, d->smem_tab, d->n_sms, vn_items);
+  d->grid_vnb = occupancy_grid(d->k_vnb, d->threads_vn, d->smem_tab, d->n_sms, vn_items);
   d->grid_misc = d->n_sms * 8; // x 256 threads: a multiple of every row length G <= 2048 (refill_kernel keeps its g)
   CU_TRY(cudaStreamSynchronize(d->stream));
   *out = d.release();

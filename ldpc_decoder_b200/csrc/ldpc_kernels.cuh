@@ -45,6 +45,19 @@ constexpr int min_blocks_for(int D) { return D <= 4 ? LDPC_MINBLOCKS_D4 : (D <= 
 // The check-node kernel with D <= 6 runs 512-thread CTAs (2 per SM instead of 4 x 256): same resident threads, half
 // the table staging and CTA turnover -- +2-3 % measured; larger D and the variable-node kernel showed no gain.
 constexpr int cn_threads_for(int D) { return D <= 6 ? 512 : kThreads; }
+#ifndef LDPC_VN_THREADS
+#define LDPC_VN_THREADS kThreads
+#endif
+constexpr int vn_threads_for(int D) { return D <= 6 ? LDPC_VN_THREADS : kThreads; }
+#ifndef LDPC_PREFETCH_F32_VN
+#define LDPC_PREFETCH_F32_VN false
+#endif
+#ifndef LDPC_PREFETCH_F16_CN
+#define LDPC_PREFETCH_F16_CN false
+#endif
+#ifndef LDPC_PREFETCH_F32_CN
+#define LDPC_PREFETCH_F32_CN false
+#endif
 constexpr int kPhiTableSize = 32768; // fp16 phi_abs table entries (all non-negative half bit patterns)
 
 // ---------------------------------------------------------------- memory helpers
@@ -127,7 +140,7 @@ struct TraitsF32 {
   static constexpr bool kUsesTable = false;
   // software prefetch of the next item's indices: measured on B200 (scripts/kernel_perf.py), it only pays in the
   // fp16 variable-node pass (+3-4 %); elsewhere the extra registers cost a resident CTA
-  static constexpr bool kPrefetchCN = false, kPrefetchVN = false;
+  static constexpr bool kPrefetchCN = LDPC_PREFETCH_F32_CN, kPrefetchVN = LDPC_PREFETCH_F32_VN;
 
   __device__ static __forceinline__ uint32_t abs_w(uint32_t w) { return w & 0x7FFFFFFFu; }
   __device__ static __forceinline__ uint32_t add_w(uint32_t a, uint32_t b) {
@@ -164,7 +177,7 @@ struct TraitsF16 {
   static constexpr int kFramesPerVec = 8;
   static constexpr uint32_t kSignMask = 0x80008000u;
   static constexpr bool kUsesTable = true;
-  static constexpr bool kPrefetchCN = false, kPrefetchVN = true;
+  static constexpr bool kPrefetchCN = LDPC_PREFETCH_F16_CN, kPrefetchVN = true;
 
   __device__ static __forceinline__ __half2 h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
   __device__ static __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(kBulkTileVec, 2)
 // phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).
 // The gather list of the thread's NEXT item is fetched while the current messages are in flight.
 template <class Tr, bool kFinalBits, int kMaxRegDeg, class Idx>
-__global__ void __launch_bounds__(kThreads, min_blocks_for(kMaxRegDeg))
+__global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMaxRegDeg) * kThreads / vn_threads_for(kMaxRegDeg))
     vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ col_ptr,
                      const uint32_t *__restrict__ in_to_out, uint8_t *__restrict__ hard,
                      const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_vars, uint32_t log2_g,

@@ -18,6 +18,11 @@ elif code_arg[0] == "banded":  # banded:log2n:dv:dc:window  (locality experiment
         sockets[b:b + win] = blk[rng.permutation(blk.size)]
     m = n * dv // dc
     gen = alist.Code(m, n, np.arange(0, m * dc + 1, dc, dtype=np.uint32), sockets.astype(np.uint32), 0)
+elif code_arg[0] == "seq":  # seq:log2n  (access-pattern experiment: a degenerate (3,6) multigraph whose variable-node
+    n = 1 << int(code_arg[1])  # gathers are as sequential as the check-node rows: variable v owns edge rows 3v..3v+2)
+    m = n // 2
+    cols = np.repeat(np.arange(n, dtype=np.uint32), 3)
+    gen = alist.Code(m, n, np.arange(0, 6 * m + 1, 6, dtype=np.uint32), cols, 0)
 else:  # reg:log2n:dv:dc
     gen = alist.make_regular_code(1 << int(code_arg[1]), int(code_arg[2]), int(code_arg[3]), seed=1)
 print("code", code_arg, "N", gen.n_vars, "M", gen.n_checks, "E", gen.n_edges, flush=True)
