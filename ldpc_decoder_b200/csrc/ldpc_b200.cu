@@ -396,27 +396,27 @@ int pick_cn_parts(const std::vector<uint32_t> &row_ptr, int max_deg) {
 }
 
 template <class Tr, class Idx> void select_for_precision(ldpc_b200_decoder *d) {
-  switch (d->cn_parts) { // long check rows: one row over 2/4/8 lanes (cn_update_split_kernel)
-  case 2: d->k_cn = dev::cn_update_split_kernel<Tr, 2>; break;
-  case 4: d->k_cn = dev::cn_update_split_kernel<Tr, 4>; break;
-  case 8: d->k_cn = dev::cn_update_split_kernel<Tr, 8>; break;
-  default: break;
-  }
-  if (d->cn_parts > 1) goto vn;
-  if (d->cn_bulk) { // experiment: bulk-async staged check-node kernel
+  // check-node pass: split-row kernel for long rows, else the bulk-async experiment if asked for, else the
+  // register-resident kernel (with its fused-refill twin)
+  if (d->cn_parts > 1) {
+    switch (d->cn_parts) {
+    case 2: d->k_cn = dev::cn_update_split_kernel<Tr, 2>; break;
+    case 4: d->k_cn = dev::cn_update_split_kernel<Tr, 4>; break;
+    default: d->k_cn = dev::cn_update_split_kernel<Tr, 8>; break;
+    }
+  } else if (d->cn_bulk) {
     switch (d->deg_cn) {
     case 4: d->k_cn = dev::cn_update_bulk_kernel<Tr, 4>; break;
     case 6: d->k_cn = dev::cn_update_bulk_kernel<Tr, 6>; break;
     default: d->k_cn = dev::cn_update_bulk_kernel<Tr, 8>; break;
     }
-    goto vn;
+  } else {
+    switch (d->deg_cn) {
+    case 4: d->k_cn = dev::cn_update_kernel<Tr, 4, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 4>; break;
+    case 6: d->k_cn = dev::cn_update_kernel<Tr, 6, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 6>; break;
+    default: d->k_cn = dev::cn_update_kernel<Tr, 8, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 8>; break;
+    }
   }
-  switch (d->deg_cn) {
-  case 4: d->k_cn = dev::cn_update_kernel<Tr, 4, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 4>; break;
-  case 6: d->k_cn = dev::cn_update_kernel<Tr, 6, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 6>; break;
-  default: d->k_cn = dev::cn_update_kernel<Tr, 8, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 8>; break;
-  }
-vn:
   switch (d->deg_vn) {
   case 4: d->k_vn = dev::vn_update_kernel<Tr, false, 4, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 4, Idx>; break;
   case 6: d->k_vn = dev::vn_update_kernel<Tr, false, 6, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 6, Idx>; break;
