@@ -207,6 +207,9 @@ uint64_t ldpc_b200_bytes_per_frame_iteration(const ldpc_b200_decoder *dec);
 
 const char *ldpc_b200_last_error(void);
 const char *ldpc_b200_version(void);
+/* sizeof of the four public structs as this library was built, in the order ldpc_b200_code_info, ldpc_b200_config,
+ * ldpc_b200_decode_params, ldpc_b200_report: a binding checks its own mirror of the layouts against them. */
+void ldpc_b200_abi_sizes(uint32_t sizes[4]);
 
 #ifdef __cplusplus
 }

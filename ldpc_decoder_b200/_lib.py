@@ -79,6 +79,7 @@ SYMBOLS = {
     "ldpc_b200_bytes_per_frame_iteration": (C.c_uint64, [C.c_void_p]),
     "ldpc_b200_last_error": (C.c_char_p, []),
     "ldpc_b200_version": (C.c_char_p, []),
+    "ldpc_b200_abi_sizes": (None, [C.POINTER(C.c_uint32)]),
 }
 
 

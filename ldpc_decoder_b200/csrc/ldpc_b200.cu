@@ -142,6 +142,13 @@ extern "C" {
 
 const char *ldpc_b200_last_error(void) { return g_last_error.c_str(); }
 const char *ldpc_b200_version(void) { return "ldpc_b200 0.1 (sm_100a)"; }
+void ldpc_b200_abi_sizes(uint32_t sizes[4]) {
+  if (!sizes) return;
+  sizes[0] = sizeof(ldpc_b200_code_info);
+  sizes[1] = sizeof(ldpc_b200_config);
+  sizes[2] = sizeof(ldpc_b200_decode_params);
+  sizes[3] = sizeof(ldpc_b200_report);
+}
 
 static ldpc_b200_status wrap_code(std::function<ldpc_code *()> make, ldpc_b200_code **out) {
   if (!out) return fail(LDPC_B200_ERR_INVALID, "null output pointer");

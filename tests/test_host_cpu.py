@@ -23,6 +23,16 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.ldpc_b200_version()
 
 
+def test_ctypes_struct_layouts_match_the_library():
+    """The Python mirror of the four public structs has the sizes the library was compiled with."""
+    import ctypes as C
+
+    sizes = (C.c_uint32 * 4)()
+    _lib.lib().ldpc_b200_abi_sizes(sizes)
+    assert list(sizes) == [C.sizeof(_lib.CodeInfo), C.sizeof(_lib.Config), C.sizeof(_lib.DecodeParams),
+                           C.sizeof(_lib.Report)]
+
+
 @pytest.mark.parametrize("name", ["reg36", "readme13", "hideg", "tiny"])
 def test_graph_tables_match_oracle_and_generator(small_codes, name):
     gen, path = small_codes[name]
