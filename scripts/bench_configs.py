@@ -45,4 +45,4 @@ for name, make, prec, log2p, load, channel, noise, imax, pool in CASES:
            "code": {"N": N, "M": M, "E": E}}
     out.append(row); print(json.dumps(row), flush=True)
     del dec, d_in, d_syn, d_ref, d_res; torch.cuda.empty_cache()
-json.dump(out, open("gpurun_out/r01_bench_other_configs.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/" + (sys.argv[1] if len(sys.argv) > 1 else "r01") + "_bench_other_configs.json", "w"), indent=1)
