@@ -789,6 +789,243 @@ ldpc_b200_status retire_frames(ldpc_b200_decoder *d, uint32_t cnt, const uint32_
 
 } // namespace
 
+// ------------------------------------------------------------------ per-launch timing
+// LDPC_B200_FLAG_TIME_KERNELS: CUDA events on the launching stream around every check-node / variable-node launch and
+// around the per-check service steps.  Two pools (periods alternate: the device runs one period ahead of the host), 3
+// events per flood iteration + 4 per service step; flush(h) adds the elapsed times of pool h to the report once the
+// host has synchronised with that period.  Without the flag every call is a no-op.
+namespace {
+
+struct launch_timer {
+  std::vector<cudaEvent_t> iter_ev[2], service_ev[2];
+  uint32_t timed_iters[2] = {0, 0};
+  cudaStream_t stream = nullptr;
+  ldpc_b200_report *rep = nullptr;
+  bool first_cn_is_fused = false, on = false;
+
+  ldpc_b200_status create(uint32_t max_iters, cudaStream_t s, ldpc_b200_report *r, bool fused) {
+    stream = s;
+    rep = r;
+    first_cn_is_fused = fused;
+    for (int h = 0; h < 2; ++h) {
+      iter_ev[h].assign(3 * size_t(max_iters), nullptr);
+      service_ev[h].assign(4, nullptr);
+      for (cudaEvent_t &e : iter_ev[h]) CU_TRY(cudaEventCreate(&e));
+      for (cudaEvent_t &e : service_ev[h]) CU_TRY(cudaEventCreate(&e));
+    }
+    on = true;
+    return LDPC_B200_OK;
+  }
+  ~launch_timer() {
+    for (int h = 0; h < 2; ++h) {
+      for (cudaEvent_t e : iter_ev[h])
+        if (e) cudaEventDestroy(e);
+      for (cudaEvent_t e : service_ev[h])
+        if (e) cudaEventDestroy(e);
+    }
+  }
+  // which: 0 before the check-node launch, 1 between the two launches, 2 after the variable-node launch
+  void mark_iter(int h, uint32_t i, int which) {
+    if (on) cudaEventRecord(iter_ev[h][3 * i + which], stream);
+  }
+  // which: 0 before the syndrome check, 1 after it, 2 after scheduler + extraction, 3 after the refill
+  void mark_service(int h, int which) {
+    if (on) cudaEventRecord(service_ev[h][which], stream);
+  }
+  void set_iters(int h, uint32_t n) {
+    if (on) timed_iters[h] = n;
+  }
+  void flush(int h) {
+    if (!on) return;
+    for (uint32_t i = 0; i < timed_iters[h]; ++i) {
+      float cn = 0, vn = 0;
+      cudaEventElapsedTime(&cn, iter_ev[h][3 * i], iter_ev[h][3 * i + 1]);
+      cudaEventElapsedTime(&vn, iter_ev[h][3 * i + 1], iter_ev[h][3 * i + 2]);
+      if (i == 0 && first_cn_is_fused) rep->cn_refill_s += cn * 1e-3; // the fused pass is timed apart from the plain ones
+      else rep->cn_s += cn * 1e-3;
+      rep->vn_s += vn * 1e-3;
+    }
+    timed_iters[h] = 0;
+    float check = 0, retire = 0, refill = 0;
+    cudaEventElapsedTime(&check, service_ev[h][0], service_ev[h][1]);
+    cudaEventElapsedTime(&retire, service_ev[h][1], service_ev[h][2]);
+    cudaEventElapsedTime(&refill, service_ev[h][2], service_ev[h][3]);
+    rep->check_s += check * 1e-3;
+    rep->retire_s += retire * 1e-3;
+    rep->refill_s += refill * 1e-3;
+  }
+};
+
+} // namespace
+
+// ------------------------------------------------------------------ scheduler constants
+// Everything dev::sched_kernel needs to know about one decode() call: the reference's batch / stop-rule parameters
+// (ldpc_decoder_gpu.cu:296-315) plus where new frames come from (input layout, staging-ring geometry).
+namespace {
+
+dev::SchedConst make_sched_const(const ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm, uint32_t n_frames,
+                                 bool in_dev, bool syn_dev, bool res_dev) {
+  dev::SchedConst sc;
+  memset(&sc, 0, sizeof(sc));
+  const uint32_t B = std::min(n_frames, d->frames_in_flight); // num_vectors_gpu_batch
+  const uint32_t n_reg = d->N - d->n_erased;
+  sc.n_frames = n_frames;
+  sc.batch = B;
+  sc.log2_p = d->log2P;
+  sc.k_check = prm->num_iter_check_parity;
+  sc.imax = prm->num_iter_max;
+  sc.simd_pairs = (prm->flags & LDPC_B200_FLAG_SIMD_PAIRS) ? 1u : 0u;
+  sc.syn_words = d->S;
+  sc.res_words = d->W;
+  sc.n_cols = prm->input_pool_frames ? prm->input_pool_frames : n_frames;
+  sc.n_regular = n_reg;
+  const bool packed = prm->input_layout == LDPC_B200_LAYOUT_PACKED_BITS;
+  const bool frame_major = prm->input_layout == LDPC_B200_LAYOUT_FRAME_MAJOR || packed;
+  sc.row_elems = packed ? (n_reg + 31) / 32 : n_reg; // per-frame elements of a frame-major input
+  sc.frame_stride = prm->frame_stride ? prm->frame_stride : sc.row_elems;
+  sc.ring_block = frame_major ? 1u : 32u; // frames per interleaved staging block (64-128 B runs)
+  // live staged frames are always inside [next_to_load, next_to_load + B) (+ block rounding)
+  sc.ring_frames = std::min<uint32_t>(d->P, ((B + sc.ring_block - 1) / sc.ring_block + 1) * sc.ring_block);
+  sc.input_mode = in_dev ? (frame_major ? 1u : 0u) : (frame_major ? 3u : 2u);
+  sc.early_retire = (prm->flags & LDPC_B200_FLAG_EARLY_RETIRE) ? 1u : 0u;
+  sc.log2_v = d->precision == LDPC_B200_FP32 ? 2u : 3u;
+  // the flood kernels need at least 32 slots, and a warp of the split-row kernel must stay inside one row
+  sc.min_log2_p_active = 5;
+  if (d->cn_parts > 1) sc.min_log2_p_active = std::max<uint32_t>(5, ilog2(32u / uint32_t(d->cn_parts)) + sc.log2_v);
+  if (d->cn_bulk) sc.min_log2_p_active = ilog2(uint32_t(dev::kBulkTileVec)) + sc.log2_v; // whole tiles only
+  sc.syn_ring = syn_dev ? 0u : 1u;
+  sc.results_ring = res_dev ? 0u : 1u;
+  return sc;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ host feed
+// Staging of host-resident frames into the device ring over the copy stream (the reference's prepare_vectors +
+// transfer_vectors, ldpc_decoder_gpu.cu:199-273, but gathered by all host threads, off the critical path and in
+// sub-ranges so that the H2D of one chunk overlaps the gather of the next).  Frames [staged, upto) are gathered into a
+// pinned mirror laid out like the ring and copied block by block; ring position of frame f: f % ring_frames.
+namespace {
+
+struct host_feeder {
+  ldpc_b200_decoder *d = nullptr;
+  ldpc_b200_report *rep = nullptr;
+  const uint8_t *in_host = nullptr;   // null: the channel values are device-resident (read in place)
+  const uint32_t *syn_host = nullptr; // null: the syndromes are device-resident
+  bool frame_major = false;
+  uint32_t n_frames = 0, n_cols = 0, n_reg = 0, ring_block = 32, ring_frames = 0, row_elems = 0;
+  size_t es = 4, es_fm = 4;  // element size of the interleaved / frame-major (or packed-bit) layouts
+  uint64_t frame_stride = 0; // frame-major inputs: elements between frames
+  uint32_t staged = 0;       // frames [0, staged) have been handed to the copy stream
+  bool refill_recorded = false;
+
+  ldpc_b200_status stage_upto(uint32_t upto) {
+    if (!in_host && !syn_host) return LDPC_B200_OK;
+    upto = std::min(n_frames, upto);
+    if (upto <= staged) return LDPC_B200_OK;
+    CU_TRY(cudaStreamSynchronize(d->copy_stream)); // earlier copies out of the pinned mirror are done
+    // ring positions being overwritten belong to frames already loaded; their refill kernels must have read them
+    if (refill_recorded) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_refilled, 0));
+    const uint32_t sub = std::max(8 * ring_block, 256u);
+    for (uint32_t f0 = staged; f0 < upto;) {
+      const uint32_t f1 = std::min(upto, (f0 / sub + 1) * sub);
+      ldpc_b200_status st = LDPC_B200_OK;
+      if (in_host) st = frame_major ? stage_frame_major(f0, f1) : stage_interleaved(f0, f1);
+      if (st == LDPC_B200_OK && syn_host) st = stage_syndromes(f0, f1);
+      if (st != LDPC_B200_OK) return st;
+      f0 = f1;
+    }
+    staged = upto;
+    CU_TRY(cudaEventRecord(d->ev_staged, d->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_staged, 0)); // the refill kernels read the ring
+    return LDPC_B200_OK;
+  }
+
+private:
+  // the reference's prepare_vectors (ldpc_decoder_gpu.cu:199-207) in blocks of ring_block frames:
+  // pinned[blk][i][0..ring_block) <- input[i][col..col+run)
+  ldpc_b200_status stage_interleaved(uint32_t f0, uint32_t f1) {
+    struct chunk_t {
+      size_t dst, src, bytes; // dst: offset of row 0 inside the pinned mirror; src: byte offset inside a row
+    };
+    std::vector<chunk_t> chunks; // the same for every variable row: computed once
+    for (uint32_t f = f0; f < f1;) {
+      const uint32_t r = f % ring_frames, in_blk = r % ring_block, col = f % n_cols;
+      const uint32_t run = std::min({f1 - f, ring_block - in_blk, n_cols - col});
+      chunks.push_back({(size_t(r / ring_block) * n_reg * ring_block + in_blk) * es, size_t(col) * es, size_t(run) * es});
+      f += run;
+    }
+    const size_t row_dst_stride = size_t(ring_block) * es, row_src_stride = size_t(n_cols) * es;
+    uint8_t *mirror = d->h_stage.p;
+    const uint8_t *src = in_host;
+    parallel_for(n_reg, d->host_threads, [&](size_t ia, size_t ib) {
+      for (size_t i = ia; i < ib; ++i) {
+        const uint8_t *row = src + i * row_src_stride;
+        uint8_t *dst_row = mirror + i * row_dst_stride;
+        for (const chunk_t &c : chunks) {
+          // whole blocks (32 frames = 64 or 128 bytes) start on a 64-byte boundary of the mirror
+          if (c.bytes == 64 && c.dst % 64 == 0) {
+            copy64_streaming(dst_row + c.dst, row + c.src);
+          } else if (c.bytes == 128 && c.dst % 128 == 0) {
+            copy64_streaming(dst_row + c.dst, row + c.src);
+            copy64_streaming(dst_row + c.dst + 64, row + c.src + 64);
+          } else {
+            memcpy(dst_row + c.dst, row + c.src, c.bytes);
+          }
+        }
+      }
+      streaming_fence(); // the streaming stores are globally visible before the DMA engine reads the mirror
+    });
+    // one H2D per touched block range (contiguous blocks in the ring)
+    for (uint32_t f = f0; f < f1;) {
+      const uint32_t r = f % ring_frames, blk0 = r / ring_block;
+      const uint32_t run = std::min(f1 - f, ring_frames - r); // up to the end of the ring
+      const uint32_t n_blk = (r % ring_block + run + ring_block - 1) / ring_block;
+      const size_t off = size_t(blk0) * n_reg * ring_block * es, bytes = size_t(n_blk) * n_reg * ring_block * es;
+      CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
+      rep->h2d_bytes += bytes;
+      f += run;
+    }
+    return LDPC_B200_OK;
+  }
+
+  // frame-major (or packed-bit) input: one contiguous row per frame
+  ldpc_b200_status stage_frame_major(uint32_t f0, uint32_t f1) {
+    uint8_t *mirror = d->h_stage.p;
+    parallel_for(f1 - f0, d->host_threads, [&](size_t a, size_t b) {
+      for (size_t t = a; t < b; ++t) {
+        const uint32_t f = f0 + uint32_t(t);
+        memcpy(mirror + size_t(f % ring_frames) * row_elems * es_fm, in_host + size_t(f % n_cols) * frame_stride * es_fm,
+               size_t(row_elems) * es_fm);
+      }
+    });
+    for (uint32_t f = f0; f < f1;) {
+      const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
+      const size_t off = size_t(r) * row_elems * es_fm, bytes = size_t(run) * row_elems * es_fm;
+      CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
+      rep->h2d_bytes += bytes;
+      f += run;
+    }
+    return LDPC_B200_OK;
+  }
+
+  ldpc_b200_status stage_syndromes(uint32_t f0, uint32_t f1) {
+    const uint32_t S = d->S;
+    for (uint32_t f = f0; f < f1; ++f)
+      memcpy(d->h_stage_syn.p + size_t(f % ring_frames) * S, syn_host + size_t(f % n_cols) * S, size_t(S) * 4);
+    for (uint32_t f = f0; f < f1;) {
+      const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
+      CU_TRY(cudaMemcpyAsync(d->d_stage_syn.p + size_t(r) * S, d->h_stage_syn.p + size_t(r) * S, size_t(run) * S * 4,
+                             cudaMemcpyHostToDevice, d->copy_stream));
+      rep->h2d_bytes += size_t(run) * S * 4;
+      f += run;
+    }
+    return LDPC_B200_OK;
+  }
+};
+
+} // namespace
+
 extern "C" {
 
 // decode(): the reference's scheduling semantics (ldpc_decoder_gpu.cu:283-634) with the decisions taken on
@@ -815,9 +1052,6 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   const bool time_kernels = (prm->flags & LDPC_B200_FLAG_TIME_KERNELS) != 0;
   const uint32_t B = std::min(n_frames, d->frames_in_flight); // num_vectors_gpu_batch
   const uint32_t k_check = prm->num_iter_check_parity;
-  const uint32_t n_reg = d->N - d->n_erased;
-  const uint32_t n_cols = prm->input_pool_frames ? prm->input_pool_frames : n_frames;
-  const size_t es = d->elem;
   // even-count refills can never load an odd remainder (the reference's OpenCL harness only ever feeds
   // parallel_factor * loading_factor frames, ldpc_decoder_gpu.cpp:623 / main.cpp:320)
   if (simd_pairs && ((n_frames - B) & 1u))
@@ -826,40 +1060,11 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   const uint64_t period_limit =
       (uint64_t(n_frames) / B + 2) * ((uint64_t(prm->num_iter_max) + 2ull * k_check + 2) / k_check + 2);
 
-  // ---- scheduler constants
-  dev::SchedConst sc;
-  memset(&sc, 0, sizeof(sc));
-  sc.n_frames = n_frames;
-  sc.batch = B;
-  sc.log2_p = d->log2P;
-  sc.k_check = k_check;
-  sc.imax = prm->num_iter_max;
-  sc.simd_pairs = simd_pairs;
-  sc.syn_words = d->S;
-  sc.res_words = d->W;
-  sc.n_cols = n_cols;
-  sc.n_regular = n_reg;
+  // ---- scheduler constants (also the geometry of the staging ring)
   const bool packed = prm->input_layout == LDPC_B200_LAYOUT_PACKED_BITS;
-  const uint32_t row_elems = packed ? (n_reg + 31) / 32 : n_reg; // per-frame elements of a frame-major input
-  const size_t es_fm = packed ? 4 : es;                          //  ... and their size
-  sc.row_elems = row_elems;
-  sc.frame_stride = prm->frame_stride ? prm->frame_stride : row_elems;
   const bool frame_major = prm->input_layout == LDPC_B200_LAYOUT_FRAME_MAJOR || packed;
-  const uint32_t ring_block = frame_major ? 1u : 32u; // frames per interleaved staging block (64-128 B runs)
-  // live staged frames are always inside [next_to_load, next_to_load + B) (+ block rounding)
-  const uint32_t ring_frames = std::min<uint32_t>(d->P, ((B + ring_block - 1) / ring_block + 1) * ring_block);
-  sc.ring_block = ring_block;
-  sc.ring_frames = ring_frames;
-  sc.input_mode = in_dev ? (frame_major ? 1u : 0u) : (frame_major ? 3u : 2u);
-  sc.early_retire = (prm->flags & LDPC_B200_FLAG_EARLY_RETIRE) ? 1u : 0u;
-  sc.log2_v = d->precision == LDPC_B200_FP32 ? 2u : 3u;
-  // the flood kernels need at least 32 slots, and a warp of the split-row kernel must stay inside one row
-  sc.min_log2_p_active = 5;
-  if (d->cn_parts > 1) sc.min_log2_p_active = std::max<uint32_t>(5, ilog2(32u / uint32_t(d->cn_parts)) + sc.log2_v);
-  if (d->cn_bulk) sc.min_log2_p_active = ilog2(uint32_t(dev::kBulkTileVec)) + sc.log2_v; // whole tiles only
-  sc.syn_ring = syn_dev ? 0u : 1u;
-  sc.results_ring = res_dev ? 0u : 1u;
-  if (!in_dev && ring_frames < std::min<uint32_t>(d->P, B + ring_block) && ring_frames < B)
+  const dev::SchedConst sc = make_sched_const(d, prm, n_frames, in_dev, syn_dev, res_dev);
+  if (!in_dev && sc.ring_frames < std::min<uint32_t>(d->P, B + sc.ring_block) && sc.ring_frames < B)
     return fail(LDPC_B200_ERR_INVALID, "staging ring too small (internal error)");
   if (!in_dev) {
     const ldpc_b200_status se = d->ensure_input_staging();
@@ -880,142 +1085,31 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   if (d->d_iter.n < 2ull * n_frames) CU_TRY(d->d_iter.alloc(2ull * n_frames));
   uint32_t *d_iter_start = d->d_iter.p, *d_iter_end = d->d_iter.p + n_frames;
 
-  // ---- staging of host-resident frames into the device ring (copy stream)
-  // frames [staged, upto) are gathered by all host threads into pinned memory laid out like the ring, then
-  // copied block by block.  Ring position of frame f: f % ring_frames.
-  uint32_t staged = 0;
-  bool refill_recorded = false;
-  const uint8_t *in_host = static_cast<const uint8_t *>(input);
-  auto stage_upto = [&](uint32_t upto) -> ldpc_b200_status {
-    if (in_dev && syn_dev) return LDPC_B200_OK;
-    upto = std::min(n_frames, upto);
-    if (upto <= staged) return LDPC_B200_OK;
-    CU_TRY(cudaStreamSynchronize(d->copy_stream)); // earlier copies out of the pinned mirror are done
-    // ring positions being overwritten belong to frames already loaded; their refill kernels must have read them
-    if (refill_recorded) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_refilled, 0));
-    const uint32_t f0_all = staged, f1_all = upto;
-    // in sub-ranges, so the H2D of one chunk overlaps the host gather of the next
-    const uint32_t sub = 8 * ring_block > 256 ? 8 * ring_block : 256;
-    for (uint32_t f0 = f0_all; f0 < f1_all;) {
-    const uint32_t f1 = std::min(f1_all, (f0 / sub + 1) * sub);
-    if (!in_dev) {
-      if (!frame_major) {
-        // the reference's prepare_vectors (ldpc_decoder_gpu.cu:199-207) in blocks of ring_block frames:
-        // pinned[blk][i][0..ring_block) <- input[i][col..col+run)
-        // chunk descriptors are the same for every variable row: compute them once
-        struct chunk_t {
-          size_t dst, src, bytes; // dst: offset of row 0 inside the pinned mirror; src: byte offset inside a row
-        };
-        std::vector<chunk_t> chunks;
-        for (uint32_t f = f0; f < f1;) {
-          const uint32_t r = f % ring_frames, in_blk = r % ring_block, col = f % n_cols;
-          const uint32_t run = std::min({f1 - f, ring_block - in_blk, n_cols - col});
-          chunks.push_back({(size_t(r / ring_block) * n_reg * ring_block + in_blk) * es, size_t(col) * es, size_t(run) * es});
-          f += run;
-        }
-        const size_t row_dst_stride = size_t(ring_block) * es, row_src_stride = size_t(n_cols) * es;
-        parallel_for(n_reg, d->host_threads, [&](size_t ia, size_t ib) {
-          for (size_t i = ia; i < ib; ++i) {
-            const uint8_t *row = in_host + i * row_src_stride;
-            uint8_t *dst_row = d->h_stage.p + i * row_dst_stride;
-            for (const chunk_t &c : chunks) {
-              // whole blocks (32 frames = 64 or 128 bytes) start on a 64-byte boundary of the mirror
-              if (c.bytes == 64 && c.dst % 64 == 0) {
-                copy64_streaming(dst_row + c.dst, row + c.src);
-              } else if (c.bytes == 128 && c.dst % 128 == 0) {
-                copy64_streaming(dst_row + c.dst, row + c.src);
-                copy64_streaming(dst_row + c.dst + 64, row + c.src + 64);
-              } else {
-                memcpy(dst_row + c.dst, row + c.src, c.bytes);
-              }
-            }
-          }
-          streaming_fence(); // the streaming stores are globally visible before the DMA engine reads the mirror
-        });
-        // one H2D per touched block range (contiguous blocks in the ring)
-        uint32_t f = f0;
-        while (f < f1) {
-          const uint32_t r = f % ring_frames;
-          const uint32_t blk0 = r / ring_block;
-          const uint32_t run = std::min(f1 - f, ring_frames - r); // up to the end of the ring
-          const uint32_t n_blk = (r % ring_block + run + ring_block - 1) / ring_block;
-          const size_t off = size_t(blk0) * n_reg * ring_block * es, bytes = size_t(n_blk) * n_reg * ring_block * es;
-          CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
-          rep.h2d_bytes += bytes;
-          f += run;
-        }
-      } else {
-        parallel_for(f1 - f0, d->host_threads, [&](size_t a, size_t b2) {
-          for (size_t t = a; t < b2; ++t) {
-            const uint32_t f = f0 + uint32_t(t);
-            memcpy(d->h_stage.p + size_t(f % ring_frames) * row_elems * es_fm,
-                   in_host + size_t(f % n_cols) * sc.frame_stride * es_fm, size_t(row_elems) * es_fm);
-          }
-        });
-        uint32_t f = f0;
-        while (f < f1) {
-          const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
-          const size_t off = size_t(r) * row_elems * es_fm, bytes = size_t(run) * row_elems * es_fm;
-          CU_TRY(cudaMemcpyAsync(d->d_stage.p + off, d->h_stage.p + off, bytes, cudaMemcpyHostToDevice, d->copy_stream));
-          rep.h2d_bytes += bytes;
-          f += run;
-        }
-      }
-    }
-    if (!syn_dev) {
-      for (uint32_t f = f0; f < f1; ++f)
-        memcpy(d->h_stage_syn.p + size_t(f % ring_frames) * d->S, syndromes + size_t(f % n_cols) * d->S,
-               size_t(d->S) * 4);
-      uint32_t f = f0;
-      while (f < f1) {
-        const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
-        CU_TRY(cudaMemcpyAsync(d->d_stage_syn.p + size_t(r) * d->S, d->h_stage_syn.p + size_t(r) * d->S,
-                               size_t(run) * d->S * 4, cudaMemcpyHostToDevice, d->copy_stream));
-        rep.h2d_bytes += size_t(run) * d->S * 4;
-        f += run;
-      }
-    }
-    f0 = f1;
-    }
-    staged = f1_all;
-    CU_TRY(cudaEventRecord(d->ev_staged, d->copy_stream));
-    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_staged, 0)); // the refill kernels read the ring
-    return LDPC_B200_OK;
-  };
+  // ---- staging of host-resident frames into the device ring (copy stream): see host_feeder
+  host_feeder feed;
+  feed.d = d;
+  feed.rep = &rep;
+  feed.in_host = in_dev ? nullptr : static_cast<const uint8_t *>(input);
+  feed.syn_host = syn_dev ? nullptr : syndromes;
+  feed.frame_major = frame_major;
+  feed.n_frames = n_frames;
+  feed.n_cols = sc.n_cols;
+  feed.n_reg = sc.n_regular;
+  feed.ring_block = sc.ring_block;
+  feed.ring_frames = sc.ring_frames;
+  feed.row_elems = sc.row_elems;
+  feed.es = d->elem;
+  feed.es_fm = packed ? 4 : d->elem;
+  feed.frame_stride = sc.frame_stride;
+  auto stage_upto = [&](uint32_t upto) { return feed.stage_upto(upto); };
 
-  // ---- optional per-launch timing: two event pools (periods alternate), 3 events per flood iteration
-  struct event_pool {
-    std::vector<cudaEvent_t> ev;
-    ~event_pool() {
-      for (cudaEvent_t e : ev) cudaEventDestroy(e);
-    }
-  } tev[2], sev[2];
-  uint32_t timed_iters[2] = {0, 0};
-  if (time_kernels)
-    for (int h = 0; h < 2; ++h) {
-      tev[h].ev.resize(3 * size_t(k_check + 1));
-      sev[h].ev.resize(4);
-      for (cudaEvent_t &e : tev[h].ev) CU_TRY(cudaEventCreate(&e));
-      for (cudaEvent_t &e : sev[h].ev) CU_TRY(cudaEventCreate(&e));
-    }
-  auto flush_timing = [&](int h) {
-    for (uint32_t i = 0; i < timed_iters[h]; ++i) {
-      float a = 0, b2 = 0;
-      cudaEventElapsedTime(&a, tev[h].ev[3 * i], tev[h].ev[3 * i + 1]);
-      cudaEventElapsedTime(&b2, tev[h].ev[3 * i + 1], tev[h].ev[3 * i + 2]);
-      if (i == 0 && d->k_cn_refill) rep.cn_refill_s += a * 1e-3; // the fused pass is timed apart from the plain ones
-      else rep.cn_s += a * 1e-3;
-      rep.vn_s += b2 * 1e-3;
-    }
-    timed_iters[h] = 0;
-    float c1 = 0, c2 = 0, c3 = 0;
-    cudaEventElapsedTime(&c1, sev[h].ev[0], sev[h].ev[1]);
-    cudaEventElapsedTime(&c2, sev[h].ev[1], sev[h].ev[2]);
-    cudaEventElapsedTime(&c3, sev[h].ev[2], sev[h].ev[3]);
-    rep.check_s += c1 * 1e-3;
-    rep.retire_s += c2 * 1e-3;
-    rep.refill_s += c3 * 1e-3;
-  };
+  // ---- optional per-launch timing (LDPC_B200_FLAG_TIME_KERNELS): see launch_timer
+  launch_timer timer;
+  if (time_kernels) {
+    const ldpc_b200_status ts = timer.create(k_check + 1, d->stream, &rep, d->k_cn_refill != nullptr);
+    if (ts != LDPC_B200_OK) return ts;
+  }
+  auto flush_timing = [&](int h) { timer.flush(h); };
 
   cudaEvent_t ev_first, ev_last;
   CU_TRY(cudaEventCreate(&ev_first));
@@ -1039,7 +1133,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   const bool fused = d->k_cn_refill != nullptr;
   d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed, !fused);
   CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
-  refill_recorded = true;
+  feed.refill_recorded = true;
   rep.other_launches += 3;
   CU_TRY(cudaGetLastError());
 
@@ -1048,22 +1142,22 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     const uint32_t n_it = period == 0 ? k_check + 1 : k_check; // g = 0..k, then k more per period (:350)
     for (uint32_t i = 0; i < n_it; ++i) {
       const bool last = i + 1 == n_it;
-      if (time_kernels) cudaEventRecord(tev[h].ev[3 * i], d->stream);
+      timer.mark_iter(h, i, 0);
       if (fused && i == 0) d->launch_cn_refill();
       else d->launch_cn();
-      if (time_kernels) cudaEventRecord(tev[h].ev[3 * i + 1], d->stream);
+      timer.mark_iter(h, i, 1);
       d->launch_vn(last);
-      if (time_kernels) cudaEventRecord(tev[h].ev[3 * i + 2], d->stream);
+      timer.mark_iter(h, i, 2);
     }
-    if (time_kernels) timed_iters[h] = n_it;
+    timer.set_iters(h, n_it);
     rep.cn_launches += n_it;
     rep.vn_launches += n_it;
     rep.cn_refill_launches += fused ? 1 : 0;
-    if (time_kernels) cudaEventRecord(sev[h].ev[0], d->stream);
+    timer.mark_service(h, 0);
     d->launch_check();
     rep.other_launches++;
     rep.n_checks_run++;
-    if (time_kernels) cudaEventRecord(sev[h].ev[1], d->stream);
+    timer.mark_service(h, 1);
   };
   // while capturing, host-visible events must be recorded as external event nodes
   bool capturing = false;
@@ -1087,11 +1181,11 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
             reinterpret_cast<uint16_t *>(d->d_msg.p), reinterpret_cast<uint16_t *>(d->d_llr0.p), d->d_syn.p,
             d->d_moves.p, d->d_n_moves.p, d->E, d->N, d->M, d->log2P);
     }
-    if (time_kernels) cudaEventRecord(sev[h].ev[2], d->stream);
+    timer.mark_service(h, 2);
     CU_TRY(record(d->ev_extracted[h]));
     d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed, !fused);
     CU_TRY(record(d->ev_refilled));
-    if (time_kernels) cudaEventRecord(sev[h].ev[3], d->stream);
+    timer.mark_service(h, 3);
     CU_TRY(cudaMemcpyAsync(d->h_summary.p + h, d->d_summary.p, sizeof(dev::SchedSummary), cudaMemcpyDeviceToHost,
                            d->stream));
     if (!res_dev)
@@ -1119,7 +1213,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     if (period > 0) {
       const int hp = int((period - 1) & 1);
       CU_TRY(cudaEventSynchronize(d->ev_period[hp])); // the host sleeps here while the next iterations run
-      if (time_kernels) flush_timing(hp);
+      flush_timing(hp);
       const dev::SchedSummary sm = d->h_summary.p[hp];
       rep.d2h_bytes += sizeof(dev::SchedSummary);
       rep.frames_refilled += sm.n_new;
