@@ -287,6 +287,7 @@ struct ldpc_b200_decoder {
   vn_fn k_vn = nullptr, k_vnb = nullptr;
   int deg_cn = 8, deg_vn = 8;
   int cn_parts = 1; // > 1: check rows are split over this many lanes
+  int fused_mode = -1; // fused refill: -1 chosen per decode() call, 0 never, 1 always (LDPC_B200_FUSED_REFILL)
   int threads_cn = dev::kThreads, threads_vn = dev::kThreads;
   bool cn_bulk = false;   // experiment (LDPC_B200_CN_BULK=1): bulk-async staged check-node kernel
   size_t smem_cn = 0;     // dynamic shared memory of the check-node kernel
@@ -448,12 +449,15 @@ ldpc_b200_status select_kernels(ldpc_b200_decoder *d) {
     if (d->k_cn_refill)
       CU_TRY(cudaFuncSetAttribute(d->k_cn_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
   }
-  // EXPERIMENT, off unless LDPC_B200_FUSED_REFILL=1: refill writes only the priors and the first check-node pass of the
-  // period builds the start messages.  Measured on B200 (bench --loading 2): bit-exact, not faster -- the fused pass
-  // holds message and prior vectors of a row at once (96 registers, 2 CTAs/SM) and loses more than the skipped
-  // message-row rewrite saves.
-  const char *fused = std::getenv("LDPC_B200_FUSED_REFILL");
-  if (!fused || atoi(fused) == 0) d->k_cn_refill = nullptr;
+  // Fused refill (refill writes only the priors, the first check-node pass of the period builds the start messages):
+  // the fused pass holds message and prior vectors of a row at once (96 registers, 2 CTAs/SM) and costs ~6 ms more
+  // than the plain pass in every period, while it saves ~9 ms in a period that refills 11 % of the slots.  Measured
+  // on B200 (bench.py, fp16 P = 4096): loading factor 8: 2349 vs 2319 Mb/s, loading factor 2: 1761 vs 1776.  So it
+  // is chosen per decode() call: on when at least two batches follow the first one (most periods refill), see
+  // ldpc_b200_decode.  LDPC_B200_FUSED_REFILL=0 / 1 forces it off / on.
+  d->fused_mode = -1;
+  if (const char *fused = std::getenv("LDPC_B200_FUSED_REFILL")) d->fused_mode = atoi(fused) != 0 ? 1 : 0;
+  if (d->fused_mode == 0) d->k_cn_refill = nullptr;
   return LDPC_B200_OK;
 }
 
@@ -1103,10 +1107,15 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   feed.frame_stride = sc.frame_stride;
   auto stage_upto = [&](uint32_t upto) { return feed.stage_upto(upto); };
 
+  // fused refill: refill_kernel writes only the priors, the first check-node pass of every period makes the start
+  // messages.  It pays when most check periods refill slots, i.e. when at least two more batches follow the first
+  // (measurements at select_kernels)
+  const bool fused = d->k_cn_refill != nullptr && (d->fused_mode == 1 || uint64_t(n_frames) >= 3ull * B);
+
   // ---- optional per-launch timing (LDPC_B200_FLAG_TIME_KERNELS): see launch_timer
   launch_timer timer;
   if (time_kernels) {
-    const ldpc_b200_status ts = timer.create(k_check + 1, d->stream, &rep, d->k_cn_refill != nullptr);
+    const ldpc_b200_status ts = timer.create(k_check + 1, d->stream, &rep, fused);
     if (ts != LDPC_B200_OK) return ts;
   }
   auto flush_timing = [&](int h) { timer.flush(h); };
@@ -1129,8 +1138,6 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   dev::sched_init_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(sc, d->d_state.p, d->d_in_gpu.p, d->d_virt.p,
                                                                   d_iter_start, d_iter_end, d->d_refill.p, d->d_n_new.p,
                                                                   d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p);
-  // fused refill: refill_kernel writes only the priors, the first check-node pass of the period makes the messages
-  const bool fused = d->k_cn_refill != nullptr;
   d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed, !fused);
   CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
   feed.refill_recorded = true;

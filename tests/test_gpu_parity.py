@@ -659,18 +659,20 @@ def test_bulk_async_check_node_kernel_is_bit_exact(prec, monkeypatch):
     ("tiny", "awgn", 0.7, 200, 5),
 ])
 def test_fused_refill_equals_stand_alone_refill(small_codes, prec, name, channel, noise, n_frames, log2p, monkeypatch):
-    """EXPERIMENT LDPC_B200_FUSED_REFILL=1: decode() writes only the priors of new frames and lets the first check-node
-    pass of the period build their start messages (cn_update_refill_kernel).  The default is the stand-alone refill
-    that writes the message rows itself (the reference's flood_refill, flood.cu:297-323): results, iteration counts
-    and the message state after a decode must be identical bit for bit, in both precisions."""
+    """Fused refill (forced with LDPC_B200_FUSED_REFILL=1; by default chosen per decode() call): decode() writes only
+    the priors of new frames and lets the first check-node pass of the period build their start messages
+    (cn_update_refill_kernel).  LDPC_B200_FUSED_REFILL=0 keeps the stand-alone refill that writes the message rows
+    itself (the reference's flood_refill, flood.cu:297-323): results, iteration counts and the message state after a
+    decode must be identical bit for bit, in both precisions."""
     gen, path = small_codes[name]
     fp16 = prec == "fp16"
     inp, syn, bits, prm = _frames(gen, n_frames, channel, noise, 5, np.float16 if fp16 else np.float32)
     ch = L.AWGN if channel == "awgn" else L.BSC
     monkeypatch.setenv("LDPC_B200_FUSED_REFILL", "1")
     a = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, log2p)
-    monkeypatch.delenv("LDPC_B200_FUSED_REFILL")
+    monkeypatch.setenv("LDPC_B200_FUSED_REFILL", "0")
     b = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, log2p)
+    monkeypatch.delenv("LDPC_B200_FUSED_REFILL")
     ra, ia, repa = a.decode(ch, prm, inp, syn, num_iter_max=50, num_iter_check_parity=5)
     rb_, ib, repb = b.decode(ch, prm, inp, syn, num_iter_max=50, num_iter_check_parity=5)
     assert repa["cn_refill_launches"] > 0 and repb["cn_refill_launches"] == 0
@@ -695,8 +697,9 @@ def test_fused_refill_long_rows(monkeypatch):
         inp, syn, bits, prm = _frames(gen, 150, "bsc", 0.01, 9, dt)
         monkeypatch.setenv("LDPC_B200_FUSED_REFILL", "1")
         a = L.Decoder(code, prec, 5)
-        monkeypatch.delenv("LDPC_B200_FUSED_REFILL")
+        monkeypatch.setenv("LDPC_B200_FUSED_REFILL", "0")
         b = L.Decoder(code, prec, 5)
+        monkeypatch.delenv("LDPC_B200_FUSED_REFILL")
         ra, ia, repa = a.decode(L.BSC, prm, inp, syn, num_iter_max=30, num_iter_check_parity=3)
         rb_, ib, _ = b.decode(L.BSC, prm, inp, syn, num_iter_max=30, num_iter_check_parity=3)
         assert repa["cn_refill_launches"] > 0
