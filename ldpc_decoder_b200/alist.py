@@ -167,3 +167,112 @@ def make_readme_shaped_code(log2_n: int = 20, seed: int = 1) -> Code:
     n2 = n_tx // 6
     classes = [(n_tx - n2, 3), (n2, 2), (e, 6)]
     return make_irregular_code(n, m, classes, n_erased=e, seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Reordering for locality
+# ---------------------------------------------------------------------------------------------------------------
+def read_alist(path: str) -> Code:
+    """Parser of the reference's dialect (src/ldpc_code.cpp:45-152), for the offline tools below: optional ``#e=`` /
+    ``#ec=`` header lines, ``M N``, an ignored line, M check degrees, N variable degrees, M rows of 1-based variable
+    indices padded with zeros.  (The decoder itself parses alists in C++: csrc/ldpc_code.cpp.)"""
+    n_erased = 0
+    with open(path) as f:
+        lines = f.read().split("\n")
+    i = 0
+    while lines[i].startswith("#"):
+        if lines[i].startswith("#e="):
+            n_erased = int(lines[i][3:])
+        i += 1
+    m, n = (int(x) for x in lines[i].split()[:2])
+    deg_c = np.array(lines[i + 2].split(), dtype=np.int64)
+    assert deg_c.size == m and len(lines[i + 3].split()) == n
+    cols = []
+    for r in range(m):
+        row = [int(x) for x in lines[i + 4 + r].split() if int(x) > 0]
+        assert len(row) == deg_c[r], f"row {r}: {len(row)} entries, degree {deg_c[r]}"
+        cols.extend(row)
+    row_ptr = np.zeros(m + 1, dtype=np.uint32)
+    np.cumsum(deg_c, out=row_ptr[1:])
+    return Code(m, n, row_ptr, np.array(cols, dtype=np.int64) - 1, n_erased)
+
+
+def gather_span(code: Code) -> np.ndarray:
+    """Per variable: distance, in message rows (check-major edge ids), between the first and the last row its
+    variable-node update gathers.  Small spans = the scattered 2-8 KB row reads of that pass stay close together
+    (worth ~3 % of the pass on B200 at 2^12 frames in flight: profiles/r05_locality_experiment.txt)."""
+    col_ptr, in_to_out = code.csc()
+    first = in_to_out[col_ptr[:-1].astype(np.int64).clip(max=max(code.n_edges - 1, 0))].astype(np.int64)
+    last = in_to_out[(col_ptr[1:].astype(np.int64) - 1).clip(min=0)].astype(np.int64)
+    deg = np.diff(col_ptr.astype(np.int64))
+    return np.where(deg > 0, last - first, 0)
+
+
+def reorder_for_locality(code: Code):
+    """Renumber checks and variables so that the edges of a variable sit in nearby message rows (reverse Cuthill-McKee
+    on the bipartite graph).  The punctured variables stay the last ``n_erased`` indices, as the decoder requires
+    (reference ldpc_decoder_gpu.cu:225).  Returns ``(new_code, var_perm, check_perm)`` with
+    ``new variable j = old variable var_perm[j]`` and ``new check i = old check check_perm[i]``: feed the decoder
+    ``input[var_perm]`` / syndrome bits ``[check_perm]`` and read decisions back through ``var_perm``
+    (:func:`permute_frames`).  The result describes the same code up to this coordinate permutation; a random
+    (expander-like) graph has no locality to find, structured ones (quasi-cyclic, spatially coupled, banded) do."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+    m, n, e = code.n_checks, code.n_vars, code.n_edges
+    rows = np.repeat(np.arange(m, dtype=np.int64), code.check_degrees())
+    cols = code.col_idx.astype(np.int64) + m  # nodes: checks 0..m-1, variables m..m+n-1
+    data = np.ones(2 * e, dtype=np.int8)
+    adj = coo_matrix((data, (np.concatenate([rows, cols]), np.concatenate([cols, rows]))), shape=(m + n, m + n)).tocsr()
+    order = np.asarray(reverse_cuthill_mckee(adj, symmetric_mode=True), dtype=np.int64)
+    check_perm = order[order < m]
+    var_order = order[order >= m] - m
+    n_tx = n - code.n_erased
+    var_perm = np.concatenate([var_order[var_order < n_tx], var_order[var_order >= n_tx]])  # punctured tail kept
+    new_index_of_var = np.empty(n, dtype=np.int64)
+    new_index_of_var[var_perm] = np.arange(n)
+    deg = code.check_degrees()[check_perm]
+    row_ptr = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(deg, out=row_ptr[1:])
+    old_rp = code.row_ptr.astype(np.int64)
+    # edges of new check i = edges of old check check_perm[i], variables renumbered and sorted inside the row
+    src = np.concatenate([np.arange(old_rp[c], old_rp[c + 1]) for c in check_perm]) if m else np.zeros(0, np.int64)
+    new_cols = new_index_of_var[code.col_idx.astype(np.int64)[src]]
+    row_of = np.repeat(np.arange(m, dtype=np.int64), deg)
+    new_cols = new_cols[np.lexsort((new_cols, row_of))]
+    return Code(m, n, row_ptr.astype(np.uint32), new_cols.astype(np.uint32), code.n_erased), var_perm, check_perm
+
+
+def permute_frames(code: Code, var_perm: np.ndarray, check_perm: np.ndarray, inp: np.ndarray, syn: np.ndarray):
+    """Inputs of the ORIGINAL code -> inputs of the reordered one.  inp: [N or N - n_erased, F] channel values
+    (element [i, v] = i-th value of frame v, the decoder's layout); syn: u32[F, ceil(M/32)] packed syndromes."""
+    n_rows = inp.shape[0]
+    new_inp = np.ascontiguousarray(inp[var_perm[:n_rows]])  # punctured tail stays last, so a truncated input still works
+    bits = np.unpackbits(np.ascontiguousarray(syn, dtype=np.uint32).view(np.uint8), axis=1, bitorder="little")
+    new_bits = np.zeros_like(bits)
+    new_bits[:, : code.n_checks] = bits[:, check_perm]
+    new_syn = np.packbits(new_bits, axis=1, bitorder="little").view(np.uint32).reshape(syn.shape)
+    return new_inp, new_syn
+
+
+def unpermute_results(var_perm: np.ndarray, results: np.ndarray) -> np.ndarray:
+    """Packed decisions of the reordered code (u32[F, N/32], LSB first) -> variable order of the original code."""
+    bits = np.unpackbits(np.ascontiguousarray(results, dtype=np.uint32).view(np.uint8), axis=1, bitorder="little")
+    out = np.empty_like(bits)
+    out[:, var_perm] = bits
+    return np.packbits(out, axis=1, bitorder="little").view(np.uint32).reshape(results.shape)
+
+
+if __name__ == "__main__":  # python -m ldpc_decoder_b200.alist reorder in.alist out.alist [perm.npz]
+    import sys
+
+    if len(sys.argv) >= 4 and sys.argv[1] == "reorder":
+        c = read_alist(sys.argv[2])
+        new, vp, cp = reorder_for_locality(c)
+        write_alist(new, sys.argv[3])
+        if len(sys.argv) > 4:
+            np.savez(sys.argv[4], var_perm=vp, check_perm=cp)
+        print(f"mean gather span {gather_span(c).mean():.0f} -> {gather_span(new).mean():.0f} rows "
+              f"(N={c.n_vars}, M={c.n_checks}, E={c.n_edges})")
+    else:
+        print(__doc__)
