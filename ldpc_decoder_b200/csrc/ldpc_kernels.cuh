@@ -482,8 +482,13 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
 
 // first check-node pass after a refill (one launch per check period): message and prior vectors of a row are both in
 // registers, so it runs 2 CTAs/SM with twice the loads in flight per thread
+// (ptxas fits the kernel into 80 and even 64 registers without spills -- LDPC_CN_REFILL_MINBLOCKS=3 / 4 -- by
+// serialising the prior gathers; not yet measured against this setting: first A/B of the next round.)
+#ifndef LDPC_CN_REFILL_MINBLOCKS
+#define LDPC_CN_REFILL_MINBLOCKS 2
+#endif
 template <class Tr, int kMaxRegDeg>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, LDPC_CN_REFILL_MINBLOCKS)
     cn_update_refill_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr,
                             const uint8_t *__restrict__ syn, const uint16_t *__restrict__ phi_table, uint32_t tab_last,
                             uint32_t n_checks, uint32_t log2_g, const uint32_t *__restrict__ done, const CnRefillArgs ra) {
