@@ -122,6 +122,11 @@ enum {
                                      * (implies plain launches instead of the CUDA graph)            */
   LDPC_B200_FLAG_NO_GRAPH = 4u,     /* launch the per-period kernel sequence directly instead of     *
                                      * replaying its CUDA graph                                      */
+  LDPC_B200_FLAG_HALF_INPUT = 16u,  /* EXTENSION ("fp16 transfer with fp32 compute"; the          *
+                                     * reference sets transfer_llr_t = llr_t "for simplicity", h/common.h:35-37):   *
+                                     * `input` holds IEEE halves although the decoder is FP32; they are widened on   *
+                                     * the device when a frame is loaded.  Same layouts, half the H2D bytes; results  *
+                                     * equal the FP32 decode of the half-rounded inputs bit for bit.                  */
   LDPC_B200_FLAG_EARLY_RETIRE = 8u  /* EXTENSION (off by default; the reference keeps every slot      *
                                      * iterating until the last frame of the call stops,              *
                                      * ldpc_decoder_gpu.cu:419-432): once the input is exhausted, a      *

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AWGN, BSC, LLR, FP16, FP32, LAYOUT_FRAME_MAJOR, LAYOUT_INTERLEAVED, LAYOUT_PACKED_BITS, FLAG_SIMD_PAIRS, FLAG_TIME_KERNELS, FLAG_NO_GRAPH, FLAG_EARLY_RETIRE  # noqa: F401
+from ._lib import AWGN, BSC, LLR, FP16, FP32, LAYOUT_FRAME_MAJOR, LAYOUT_INTERLEAVED, LAYOUT_PACKED_BITS, FLAG_SIMD_PAIRS, FLAG_TIME_KERNELS, FLAG_NO_GRAPH, FLAG_EARLY_RETIRE, FLAG_HALF_INPUT  # noqa: F401
 
 
 class LdpcError(RuntimeError):
@@ -135,7 +135,8 @@ class Decoder:
         """inputs/syndromes/results: numpy arrays (host) or torch CUDA tensors (device resident).
         Returns (results, iter_counts, report dict)."""
         if isinstance(inputs, np.ndarray):
-            inputs = np.ascontiguousarray(inputs, dtype=np.uint32 if layout == LAYOUT_PACKED_BITS else self.np_dtype)
+            in_dtype = np.uint32 if layout == LAYOUT_PACKED_BITS else (np.float16 if flags & FLAG_HALF_INPUT else self.np_dtype)
+            inputs = np.ascontiguousarray(inputs, dtype=in_dtype)
             if n_frames is None:
                 n_frames = inputs.shape[1] if layout == LAYOUT_INTERLEAVED else inputs.shape[0]
         if isinstance(syndromes, np.ndarray):

@@ -18,6 +18,7 @@ FLAG_SIMD_PAIRS = 1
 FLAG_TIME_KERNELS = 2
 FLAG_NO_GRAPH = 4
 FLAG_EARLY_RETIRE = 8
+FLAG_HALF_INPUT = 16
 
 
 class CodeInfo(C.Structure):

@@ -53,12 +53,15 @@ template <typename T> struct dev_buf { // RAII device allocation
   size_t n = 0;
   cudaError_t alloc(size_t count) {
     release();
-    n = count;
-    return cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    const cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count; // a failed allocation leaves an empty buffer (p == nullptr, n == 0)
+    else p = nullptr;
+    return e;
   }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
+    n = 0;
   }
   ~dev_buf() { release(); }
 };
@@ -68,12 +71,15 @@ template <typename T> struct pinned_buf { // RAII pinned host allocation
   size_t n = 0;
   cudaError_t alloc(size_t count) {
     release();
-    n = count;
-    return cudaMallocHost(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    const cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    else p = nullptr;
+    return e;
   }
   void release() {
     if (p) cudaFreeHost(p);
     p = nullptr;
+    n = 0;
   }
   ~pinned_buf() { release(); }
 };
@@ -221,6 +227,7 @@ struct ldpc_b200_decoder {
   unsigned host_threads = 1;
 
   dev_buf<uint32_t> d_row_ptr, d_col_ptr, d_in_to_out, d_edge_var;
+  dev_buf<uint32_t> d_vn_ell; // padded gather list per variable of the variable-node pass (dev::vn_fetch_list)
   dev_buf<uint8_t> d_msg, d_llr0, d_stage;
   dev_buf<uint32_t> d_syn, d_hard, d_viol, d_stage_syn, d_retire_mask, d_new_mask, d_slot_entry, d_results;
   dev_buf<dev::RefillEntry> d_refill;
@@ -277,36 +284,38 @@ struct ldpc_b200_decoder {
   // ---- launches -----------------------------------------------------------
   // kernel instantiations are chosen once per decoder (precision, register-resident degree D)
   typedef void (*cn_fn)(uint4 *, const uint32_t *, const uint8_t *, const uint16_t *, uint32_t, uint32_t, uint32_t,
-                        const uint32_t *);
+                        const uint32_t *, uint32_t);
   typedef void (*vn_fn)(uint4 *, const uint4 *, const uint32_t *, const uint32_t *, uint8_t *, const uint16_t *,
                         uint32_t, uint32_t, uint32_t, const uint32_t *);
   typedef void (*cn_refill_fn)(uint4 *, const uint32_t *, const uint8_t *, const uint16_t *, uint32_t, uint32_t,
-                               uint32_t, const uint32_t *, const dev::CnRefillArgs);
+                               uint32_t, const uint32_t *, const dev::CnRefillArgs, uint32_t);
   cn_fn k_cn = nullptr;
   cn_refill_fn k_cn_refill = nullptr; // fused refill: first check-node pass of a period (null: refill writes the messages)
   vn_fn k_vn = nullptr, k_vnb = nullptr;
   int deg_cn = 8, deg_vn = 8;
   int cn_parts = 1; // > 1: check rows are split over this many lanes
-  int fused_mode = -1; // fused refill: -1 chosen per decode() call, 0 never, 1 always (LDPC_B200_FUSED_REFILL)
+  int fused_mode = -1; // fused refill: -1 chosen per check period on the device, 0 never, 1 always (LDPC_B200_FUSED_REFILL)
+  uint32_t fused_min_pct = 6; // -1 mode: a period fuses when it loads at least this share of the slots (LDPC_B200_FUSED_MIN_PCT)
   int threads_cn = dev::kThreads, threads_vn = dev::kThreads;
   bool cn_bulk = false;   // experiment (LDPC_B200_CN_BULK=1): bulk-async staged check-node kernel
   size_t smem_cn = 0;     // dynamic shared memory of the check-node kernel
-  void launch_cn() {
+  // gate (dev::kGate*): run always / only in a period whose refill is fused / only in a period whose refill is not
+  void launch_cn(uint32_t gate = dev::kGateNone) {
     k_cn<<<grid_cn, threads_cn, smem_cn, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
                                                       reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
-                                                      tab_last, M, log2G, done_flag());
+                                                      tab_last, M, log2G, done_flag(), gate);
   }
   // first check-node pass after refill_kernel<.., kMsgRows = false>: start messages of the new slots come from the priors
-  void launch_cn_refill() {
+  void launch_cn_refill(uint32_t gate = dev::kGateNone) {
     const dev::CnRefillArgs ra{reinterpret_cast<const uint4 *>(d_llr0.p), d_edge_var.p,
                                reinterpret_cast<const uint8_t *>(d_new_mask.p)};
     k_cn_refill<<<grid_cn_refill, dev::kThreads, smem_tab, stream>>>(
         reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p, reinterpret_cast<const uint8_t *>(d_syn.p), d_phi_table.p,
-        tab_last, M, log2G, done_flag(), ra);
+        tab_last, M, log2G, done_flag(), ra, gate);
   }
   void launch_vn(bool bits) {
     (bits ? k_vnb : k_vn)<<<bits ? grid_vnb : grid_vn, threads_vn, smem_tab, stream>>>(
-        reinterpret_cast<uint4 *>(d_msg.p), reinterpret_cast<const uint4 *>(d_llr0.p), d_col_ptr.p, d_in_to_out.p,
+        reinterpret_cast<uint4 *>(d_msg.p), reinterpret_cast<const uint4 *>(d_llr0.p), d_vn_ell.p, d_in_to_out.p,
         reinterpret_cast<uint8_t *>(d_hard.p), d_phi_table.p, tab_last, N, log2G, done_flag());
   }
   void launch_check() {
@@ -315,28 +324,37 @@ struct ldpc_b200_decoder {
                                                                         d_viol.p, M, log2PW, done_flag());
   }
   // refill kernels: entries, count, masks are already in device memory (scheduler kernel or host upload)
-  void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param, int packed = 0,
-                             bool msg_rows = true) {
+  void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param, int src_kind = 0,
+                             bool msg_rows = true, uint32_t gate = dev::kGateNone, bool with_syndromes = true) {
     const uint32_t n_regular = N - n_erased;
     uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p), *l0 = reinterpret_cast<uint4 *>(d_llr0.p);
     auto launch = [&](auto kernel, const uint16_t *table) {
       kernel<<<grid_misc, dev::kThreads, 0, stream>>>(msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p,
                                                       d_col_ptr.p, d_in_to_out.p, table, N, n_regular, log2G, channel,
-                                                      param);
+                                                      param, done_flag(), gate);
     };
+    // src_kind: dev::kSrcNative / kSrcPackedBits / kSrcHalf (half elements into an fp32 decoder)
     if (precision == LDPC_B200_FP32) {
-      if (packed) msg_rows ? launch(dev::refill_kernel<dev::TraitsF32, true, true>, nullptr)
-                           : launch(dev::refill_kernel<dev::TraitsF32, true, false>, nullptr);
-      else msg_rows ? launch(dev::refill_kernel<dev::TraitsF32, false, true>, nullptr)
-                    : launch(dev::refill_kernel<dev::TraitsF32, false, false>, nullptr);
+      if (src_kind == dev::kSrcPackedBits)
+        msg_rows ? launch(dev::refill_kernel<dev::TraitsF32, dev::kSrcPackedBits, true>, nullptr)
+                 : launch(dev::refill_kernel<dev::TraitsF32, dev::kSrcPackedBits, false>, nullptr);
+      else if (src_kind == dev::kSrcHalf)
+        msg_rows ? launch(dev::refill_kernel<dev::TraitsF32, dev::kSrcHalf, true>, nullptr)
+                 : launch(dev::refill_kernel<dev::TraitsF32, dev::kSrcHalf, false>, nullptr);
+      else
+        msg_rows ? launch(dev::refill_kernel<dev::TraitsF32, dev::kSrcNative, true>, nullptr)
+                 : launch(dev::refill_kernel<dev::TraitsF32, dev::kSrcNative, false>, nullptr);
     } else {
-      if (packed) msg_rows ? launch(dev::refill_kernel<dev::TraitsF16, true, true>, d_phi_table.p)
-                           : launch(dev::refill_kernel<dev::TraitsF16, true, false>, d_phi_table.p);
-      else msg_rows ? launch(dev::refill_kernel<dev::TraitsF16, false, true>, d_phi_table.p)
-                    : launch(dev::refill_kernel<dev::TraitsF16, false, false>, d_phi_table.p);
+      if (src_kind == dev::kSrcPackedBits)
+        msg_rows ? launch(dev::refill_kernel<dev::TraitsF16, dev::kSrcPackedBits, true>, d_phi_table.p)
+                 : launch(dev::refill_kernel<dev::TraitsF16, dev::kSrcPackedBits, false>, d_phi_table.p);
+      else
+        msg_rows ? launch(dev::refill_kernel<dev::TraitsF16, dev::kSrcNative, true>, d_phi_table.p)
+                 : launch(dev::refill_kernel<dev::TraitsF16, dev::kSrcNative, false>, d_phi_table.p);
     }
-    dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
-                                                                         d_new_mask.p, d_slot_entry.p, M, log2PW);
+    if (with_syndromes)
+      dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
+                                                                           d_new_mask.p, d_slot_entry.p, M, log2PW);
   }
   // host-built entries (kernel-level entry points): h_refill[0..n) -> device, then the same kernels
   void launch_refill(uint32_t n_new, const void *src, const uint32_t *src_syn, int channel, float param) {
@@ -420,9 +438,9 @@ template <class Tr, class Idx> void select_for_precision(ldpc_b200_decoder *d) {
     }
   } else {
     switch (d->deg_cn) {
-    case 4: d->k_cn = dev::cn_update_kernel<Tr, 4, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 4>; break;
-    case 6: d->k_cn = dev::cn_update_kernel<Tr, 6, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 6>; break;
-    default: d->k_cn = dev::cn_update_kernel<Tr, 8, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 8>; break;
+    case 4: d->k_cn = dev::cn_update_kernel<Tr, 4, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 4, Idx>; break;
+    case 6: d->k_cn = dev::cn_update_kernel<Tr, 6, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 6, Idx>; break;
+    default: d->k_cn = dev::cn_update_kernel<Tr, 8, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 8, Idx>; break;
     }
   }
   switch (d->deg_vn) {
@@ -450,13 +468,15 @@ ldpc_b200_status select_kernels(ldpc_b200_decoder *d) {
       CU_TRY(cudaFuncSetAttribute(d->k_cn_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_tab)));
   }
   // Fused refill (refill writes only the priors, the first check-node pass of the period builds the start messages):
-  // the fused pass holds message and prior vectors of a row at once (96 registers, 2 CTAs/SM) and costs ~6 ms more
-  // than the plain pass in every period, while it saves ~9 ms in a period that refills 11 % of the slots.  Measured
-  // on B200 (bench.py, fp16 P = 4096): loading factor 8: 2349 vs 2319 Mb/s, loading factor 2: 1761 vs 1776.  So it
-  // is chosen per decode() call: on when at least two batches follow the first one (most periods refill), see
-  // ldpc_b200_decode.  LDPC_B200_FUSED_REFILL=0 / 1 forces it off / on.
+  // the fused pass holds message and prior vectors of a row at once and costs a few ms more than the plain pass, while
+  // it saves ~9 ms in a period that refills 11 % of the slots (measurements: profiles/README.md).  It is therefore
+  // chosen PER CHECK PERIOD ON THE DEVICE: the scheduler kernel knows how many frames the period loads and sets
+  // SchedState::fused_now when that is at least fused_min_pct % of the slots; both variants of the refill and of the
+  // period's first check-node pass are enqueued and the one not chosen exits at once (dev::gated_off).
+  // LDPC_B200_FUSED_REFILL=0 / 1 forces it off / on for every period that loads frames.
   d->fused_mode = -1;
   if (const char *fused = std::getenv("LDPC_B200_FUSED_REFILL")) d->fused_mode = atoi(fused) != 0 ? 1 : 0;
+  if (const char *pct = std::getenv("LDPC_B200_FUSED_MIN_PCT")) d->fused_min_pct = uint32_t(std::max(0, atoi(pct)));
   if (d->fused_mode == 0) d->k_cn_refill = nullptr;
   return LDPC_B200_OK;
 }
@@ -520,7 +540,7 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   // messages + priors + staging + bit-sliced syndromes/decisions + packed results
   size_t free_b = 0, total_b = 0;
   CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-  const uint64_t graph_bytes = 4ull * (uint64_t(d->M) + d->N + 2ull * d->E + 2);
+  const uint64_t graph_bytes = 4ull * (uint64_t(d->M) + 13ull * d->N + 2ull * d->E + 2);
   const uint64_t per_frame = uint64_t(d->elem) * (uint64_t(d->E) + 2ull * d->N) + 2ull * (d->M >> 3) + 8ull * d->S +
                              (d->N >> 3) * 2ull + 64;
   const uint32_t headroom = cfg->mem_headroom_pct ? cfg->mem_headroom_pct : 10;
@@ -619,6 +639,20 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   }
   st_sel = select_kernels(d.get());
   if (st_sel != LDPC_B200_OK) return st_sel;
+  { // gather list of the variable-node pass: [degree, rows of the first D edges (CSC order), ..., col_ptr[v]] per variable
+    const int D = d->deg_vn == 4 ? 4 : (d->deg_vn == 6 ? 6 : 8), W = D <= 6 ? 8 : 12; // as select_for_precision
+    const std::vector<uint32_t> &cp = code.col_ptr(), &i2o = code.in_to_out();
+    std::vector<uint32_t> ell(size_t(d->N) * W, 0u);
+    for (uint32_t v = 0; v < d->N; ++v) {
+      uint32_t *e = &ell[size_t(v) * W];
+      const uint32_t deg = cp[v + 1] - cp[v];
+      e[0] = deg;
+      for (uint32_t k = 0; k < std::min<uint32_t>(deg, uint32_t(D)); ++k) e[1 + k] = i2o[cp[v] + k];
+      e[W - 1] = cp[v];
+    }
+    CU_TRY(d->d_vn_ell.alloc(ell.size()));
+    CU_TRY(cudaMemcpy(d->d_vn_ell.p, ell.data(), ell.size() * 4, cudaMemcpyHostToDevice));
+  }
   d->threads_cn = d->cn_parts > 1 ? dev::kThreads : dev::cn_threads_for(d->deg_cn);
   d->smem_cn = d->smem_tab;
   if (d->cn_bulk) {
@@ -805,12 +839,11 @@ struct launch_timer {
   uint32_t timed_iters[2] = {0, 0};
   cudaStream_t stream = nullptr;
   ldpc_b200_report *rep = nullptr;
-  bool first_cn_is_fused = false, on = false;
+  bool on = false;
 
-  ldpc_b200_status create(uint32_t max_iters, cudaStream_t s, ldpc_b200_report *r, bool fused) {
+  ldpc_b200_status create(uint32_t max_iters, cudaStream_t s, ldpc_b200_report *r) {
     stream = s;
     rep = r;
-    first_cn_is_fused = fused;
     for (int h = 0; h < 2; ++h) {
       iter_ev[h].assign(3 * size_t(max_iters), nullptr);
       service_ev[h].assign(4, nullptr);
@@ -839,7 +872,8 @@ struct launch_timer {
   void set_iters(int h, uint32_t n) {
     if (on) timed_iters[h] = n;
   }
-  void flush(int h) {
+  // first_cn_is_fused: the first check-node pass of these iterations was the fused one (timed apart)
+  void flush(int h, bool first_cn_is_fused) {
     if (!on) return;
     for (uint32_t i = 0; i < timed_iters[h]; ++i) {
       float cn = 0, vn = 0;
@@ -1060,6 +1094,9 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   // parallel_factor * loading_factor frames, ldpc_decoder_gpu.cpp:623 / main.cpp:320)
   if (simd_pairs && ((n_frames - B) & 1u))
     return fail(LDPC_B200_ERR_INVALID, "SIMD_PAIRS needs an even number of frames beyond the first batch");
+  // with one frame in flight an even-count refill is always empty: nothing beyond the first frame could ever be loaded
+  if (simd_pairs && B < 2 && n_frames > B)
+    return fail(LDPC_B200_ERR_INVALID, "SIMD_PAIRS needs at least two frames in flight to load frames beyond the first");
   // no frame may stay longer than num_iter_max + one check period, so this bounds the whole run
   const uint64_t period_limit =
       (uint64_t(n_frames) / B + 2) * ((uint64_t(prm->num_iter_max) + 2ull * k_check + 2) / k_check + 2);
@@ -1067,7 +1104,16 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   // ---- scheduler constants (also the geometry of the staging ring)
   const bool packed = prm->input_layout == LDPC_B200_LAYOUT_PACKED_BITS;
   const bool frame_major = prm->input_layout == LDPC_B200_LAYOUT_FRAME_MAJOR || packed;
-  const dev::SchedConst sc = make_sched_const(d, prm, n_frames, in_dev, syn_dev, res_dev);
+  // fp16 transfer with fp32 compute: the input holds IEEE halves, the refill kernel widens them
+  const bool half_input = (prm->flags & LDPC_B200_FLAG_HALF_INPUT) != 0 && !packed;
+  if (half_input && d->precision != LDPC_B200_FP32)
+    return fail(LDPC_B200_ERR_INVALID, "HALF_INPUT is the transfer format of an FP32 decoder (an FP16 decoder takes halves anyway)");
+  const int src_kind = packed ? dev::kSrcPackedBits : (half_input ? dev::kSrcHalf : dev::kSrcNative);
+  dev::SchedConst sc = make_sched_const(d, prm, n_frames, in_dev, syn_dev, res_dev);
+  // fused refill, decided per period by the scheduler kernel (see select_kernels): threshold in frames
+  sc.fused_min_new = 0xFFFFFFFFu;
+  if (d->k_cn_refill) sc.fused_min_new = d->fused_mode == 1 ? 1u : std::max<uint32_t>(1u, uint32_t(uint64_t(d->P) * d->fused_min_pct / 100));
+  const bool fused_any = sc.fused_min_new != 0xFFFFFFFFu; // both variants are enqueued, the device picks
   if (!in_dev && sc.ring_frames < std::min<uint32_t>(d->P, B + sc.ring_block) && sc.ring_frames < B)
     return fail(LDPC_B200_ERR_INVALID, "staging ring too small (internal error)");
   if (!in_dev) {
@@ -1086,7 +1132,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   const uint32_t *syn_src_dev = syn_dev ? syndromes : d->d_stage_syn.p;
   uint32_t *res_dst_dev = res_dev ? results : d->d_results.p;
 
-  if (d->d_iter.n < 2ull * n_frames) CU_TRY(d->d_iter.alloc(2ull * n_frames));
+  if (!d->d_iter.p || d->d_iter.n < 2ull * n_frames) CU_TRY(d->d_iter.alloc(2ull * n_frames));
   uint32_t *d_iter_start = d->d_iter.p, *d_iter_end = d->d_iter.p + n_frames;
 
   // ---- staging of host-resident frames into the device ring (copy stream): see host_feeder
@@ -1102,23 +1148,20 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   feed.ring_block = sc.ring_block;
   feed.ring_frames = sc.ring_frames;
   feed.row_elems = sc.row_elems;
-  feed.es = d->elem;
-  feed.es_fm = packed ? 4 : d->elem;
+  feed.es = half_input ? 2 : d->elem;
+  feed.es_fm = packed ? 4 : (half_input ? 2 : d->elem);
   feed.frame_stride = sc.frame_stride;
   auto stage_upto = [&](uint32_t upto) { return feed.stage_upto(upto); };
-
-  // fused refill: refill_kernel writes only the priors, the first check-node pass of every period makes the start
-  // messages.  It pays when most check periods refill slots, i.e. when at least two more batches follow the first
-  // (measurements at select_kernels)
-  const bool fused = d->k_cn_refill != nullptr && (d->fused_mode == 1 || uint64_t(n_frames) >= 3ull * B);
 
   // ---- optional per-launch timing (LDPC_B200_FLAG_TIME_KERNELS): see launch_timer
   launch_timer timer;
   if (time_kernels) {
-    const ldpc_b200_status ts = timer.create(k_check + 1, d->stream, &rep, fused);
+    const ldpc_b200_status ts = timer.create(k_check + 1, d->stream, &rep);
     if (ts != LDPC_B200_OK) return ts;
   }
-  auto flush_timing = [&](int h) { timer.flush(h); };
+  // whether the first check-node pass of the iterations in timer pool h was the fused one (known from the summaries)
+  bool first_cn_fused[2] = {B >= sc.fused_min_new, false};
+  auto flush_timing = [&](int h) { timer.flush(h, first_cn_fused[h]); };
 
   cudaEvent_t ev_first, ev_last;
   CU_TRY(cudaEventCreate(&ev_first));
@@ -1138,32 +1181,50 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   dev::sched_init_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(sc, d->d_state.p, d->d_in_gpu.p, d->d_virt.p,
                                                                   d_iter_start, d_iter_end, d->d_refill.p, d->d_n_new.p,
                                                                   d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p);
-  d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed, !fused);
+  auto enqueue_refill = [&]() {
+    if (fused_any) {
+      d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, false, dev::kGateFused, true);
+      d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, true, dev::kGatePlain, false);
+    } else {
+      d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, true);
+    }
+  };
+  enqueue_refill();
   CU_TRY(cudaEventRecord(d->ev_refilled, d->stream));
   feed.refill_recorded = true;
-  rep.other_launches += 3;
+  rep.other_launches += 3 + (fused_any ? 1 : 0);
+  rep.cn_refill_launches += first_cn_fused[0] ? 1 : 0;
   CU_TRY(cudaGetLastError());
 
+  // launch accounting of one period (shared by the plain-launch and graph-replay paths): the gated launch that
+  // exits at once is counted with the service launches
+  auto count_iterations = [&](uint32_t n_it) {
+    rep.cn_launches += n_it;
+    rep.vn_launches += n_it;
+    rep.other_launches += 1 + (fused_any ? 1 : 0); // syndrome check (+ the gated-off check-node variant)
+    rep.n_checks_run++;
+  };
+  auto count_service = [&]() { rep.other_launches += 4 + sc.early_retire + (fused_any ? 1 : 0); };
   auto enqueue_iterations = [&](uint64_t period) {
     const int h = int(period & 1);
     const uint32_t n_it = period == 0 ? k_check + 1 : k_check; // g = 0..k, then k more per period (:350)
     for (uint32_t i = 0; i < n_it; ++i) {
       const bool last = i + 1 == n_it;
       timer.mark_iter(h, i, 0);
-      if (fused && i == 0) d->launch_cn_refill();
-      else d->launch_cn();
+      if (fused_any && i == 0) { // the device runs exactly one of the two (SchedState::fused_now)
+        d->launch_cn_refill(dev::kGateFused);
+        d->launch_cn(dev::kGatePlain);
+      } else {
+        d->launch_cn();
+      }
       timer.mark_iter(h, i, 1);
       d->launch_vn(last);
       timer.mark_iter(h, i, 2);
     }
     timer.set_iters(h, n_it);
-    rep.cn_launches += n_it;
-    rep.vn_launches += n_it;
-    rep.cn_refill_launches += fused ? 1 : 0;
+    count_iterations(n_it);
     timer.mark_service(h, 0);
     d->launch_check();
-    rep.other_launches++;
-    rep.n_checks_run++;
     timer.mark_service(h, 1);
   };
   // while capturing, host-visible events must be recorded as external event nodes
@@ -1190,7 +1251,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     }
     timer.mark_service(h, 2);
     CU_TRY(record(d->ev_extracted[h]));
-    d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, packed, !fused);
+    enqueue_refill();
     CU_TRY(record(d->ev_refilled));
     timer.mark_service(h, 3);
     CU_TRY(cudaMemcpyAsync(d->h_summary.p + h, d->d_summary.p, sizeof(dev::SchedSummary), cudaMemcpyDeviceToHost,
@@ -1199,7 +1260,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       CU_TRY(cudaMemcpyAsync(d->h_retired.p + size_t(h) * d->P, d->d_retired.p, sizeof(uint32_t) * B,
                              cudaMemcpyDeviceToHost, d->stream));
     CU_TRY(record(d->ev_period[h]));
-    rep.other_launches += 4 + sc.early_retire;
+    count_service();
     return LDPC_B200_OK;
   };
 
@@ -1225,6 +1286,8 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       rep.d2h_bytes += sizeof(dev::SchedSummary);
       rep.frames_refilled += sm.n_new;
       next_known = sm.next_to_load;
+      first_cn_fused[int(period & 1)] = sm.fused != 0; // the iterations that follow this service
+      rep.cn_refill_launches += sm.fused ? 1 : 0;
       if (!res_dev && sm.n_retired) { // drain the result ring of period-1 on the copy stream
         const size_t bytes = size_t(sm.n_retired) * d->W * 4;
         CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_extracted[hp], 0));
@@ -1280,11 +1343,8 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     } else if (use_graph) {
       CU_TRY(cudaGraphLaunch(graphs.exec[hg], d->stream));
       rep.graph_launches++;
-      rep.cn_launches += k_check;
-      rep.vn_launches += k_check;
-      rep.cn_refill_launches += fused ? 1 : 0;
-      rep.other_launches += 5 + sc.early_retire;
-      rep.n_checks_run++;
+      count_service();
+      count_iterations(k_check);
     } else {
       st = enqueue_service(period);
       if (st != LDPC_B200_OK) return st;
@@ -1303,8 +1363,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   // the run-ahead period was enqueued but did no work
   rep.cn_launches -= k_check;
   rep.vn_launches -= k_check;
-  rep.cn_refill_launches -= fused ? 1 : 0;
-  rep.other_launches -= 1;
+  rep.other_launches -= 1 + (fused_any ? 1 : 0);
   rep.n_checks_run -= 1;
 
   // per-frame iteration counters live on the device (:616-628)

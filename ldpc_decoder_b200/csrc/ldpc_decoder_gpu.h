@@ -11,7 +11,7 @@
 //  * CUDA failures throw instead of calling exit() (cuda_manager.h:13-19).
 #pragma once
 
-#include "../../include/ldpc_b200.h"
+#include "../../include/ldpc_b200_dropin.hpp"
 #include "channel.h"
 #include "common.h"
 #include "ldpc_code.h"
@@ -64,87 +64,20 @@ struct test_report {
   ldpc_b200_report device_report = ldpc_b200_report();
 };
 
-class ldpc_decoder_gpu {
-public:
-  ldpc_decoder_gpu(const ldpc_code &p_code, const noisy_channel &p_channel,
-                   const ldpc_decoder_gpu_static_parameters &p_params)
-      : m_channel(p_channel) {
-    ldpc_b200_code *code = nullptr;
-    check(ldpc_b200_code_from_csr(uint32_t(p_code.n_outputs()), uint32_t(p_code.n_inputs()), p_code.row_ptr().data(),
-                                  p_code.out_edge_to_var().data(), uint32_t(p_code.n_erased_inputs()), &code));
-    ldpc_b200_config cfg = ldpc_b200_config();
-    cfg.precision = p_params.m_use_float16 ? LDPC_B200_FP16 : LDPC_B200_FP32;
-    cfg.max_log2_frames = p_params.m_max_log_parallel_factor_user;
-    cfg.device = p_params.m_device;
-    const ldpc_b200_status st = ldpc_b200_decoder_create(code, &cfg, &m_dec);
-    ldpc_b200_code_destroy(code); // the decoder copied the tables (as the reference does, ldpc_decoder_gpu.cu:34-65)
-    check(st);
-    check(ldpc_b200_decoder_prepare_host_io(m_dec)); // this API is always fed from host arrays
-    m_parallel_factor = ldpc_b200_decoder_frames_in_flight(m_dec);
-  }
-  ~ldpc_decoder_gpu() { ldpc_b200_decoder_destroy(m_dec); }
-
-  ldpc_decoder_gpu() = delete;
-  ldpc_decoder_gpu(const ldpc_decoder_gpu &) = delete;
-  ldpc_decoder_gpu &operator=(const ldpc_decoder_gpu &) = delete;
-
-  // p_input[v + num_vectors*i] = i-th channel value of vector v (llr_t: float, or IEEE half when fp16);
-  // p_syndromes frame-major u32[ceil(M/32)] per vector; p_results frame-major u32[N/32] per vector, LSB first.
-  void decode(const ldpc_decoder_gpu_dynamic_parameters &p_dyn_params, uint32_t p_num_vectors_to_process,
-              void *p_input, const uint32_t *p_syndromes, uint32_t *p_results, test_report &report,
-              uint32_t p_log = 0) {
-    (void)p_log;
-    ldpc_b200_decode_params prm = ldpc_b200_decode_params();
-    switch (m_channel.channel()) { // transfer_vectors' dispatch, ldpc_decoder_gpu.cu:233-256
-    case bsc: {
-      const bsc_channel *cc = dynamic_cast<const bsc_channel *>(&m_channel);
-      if (!cc) throw error("channel reports bsc but is not a bsc_channel");
-      prm.channel = LDPC_B200_BSC;
-      prm.channel_param = cc->ref_llr();
-      break;
-    }
-    case awgn: {
-      const biawgn_channel *cc = dynamic_cast<const biawgn_channel *>(&m_channel);
-      if (!cc) throw error("channel reports awgn but is not a biawgn_channel");
-      prm.channel = LDPC_B200_AWGN;
-      prm.channel_param = cc->factor();
-      break;
-    }
-    default: // decoding_input_is_llr(): the caller already converted with channel.llr()
-      prm.channel = LDPC_B200_LLR;
-      prm.channel_param = 0;
-    }
-    prm.num_iter_max = p_dyn_params.m_num_iter_max;
-    prm.num_iter_check_parity = p_dyn_params.m_num_iter_check_parity;
-    prm.input_layout = LDPC_B200_LAYOUT_INTERLEAVED;
-    ldpc_b200_report rep;
-    check(ldpc_b200_decode(m_dec, &prm, p_num_vectors_to_process, p_input, p_syndromes, p_results, &rep, nullptr));
-    if (p_num_vectors_to_process == 0) return;
-    report.max_iter = rep.max_iter;
-    report.min_iter = rep.min_iter;
-    report.avg_iter = rep.avg_iter;
-    report.iter_time_per_vector = rep.iter_time_per_vector;
-    report.device_report = rep;
-  }
-
-  bool decoding_input_is_llr() const { // h/ldpc_decoder_gpu.h:112-118
-    const bool has_kernel_for_llr_conversion = (m_channel.channel() == bsc) || (m_channel.channel() == awgn);
-    return !has_kernel_for_llr_conversion;
-  }
-  uint32_t parallel_factor() const { return m_parallel_factor; }
-  void set_erased_variables(unsigned int p_n_erased_inputs) {
-    ldpc_b200_decoder_set_erased_vars(m_dec, p_n_erased_inputs);
-  }
-  ldpc_b200_decoder *handle() { return m_dec; }
-
-private:
-  static void check(ldpc_b200_status st) {
-    if (st != LDPC_B200_OK) throw error(std::string(ldpc_b200_last_error()));
-  }
-  ldpc_b200_decoder *m_dec = nullptr;
-  uint32_t m_parallel_factor = 0;
-  const noisy_channel &m_channel; // must outlive the decoder, as in the reference
+// the class itself is include/ldpc_b200_dropin.hpp, instantiated on this namespace's mirror types (the reference-tree
+// instantiation, in the global namespace, is include/ldpc_decoder_gpu.h)
+struct mirror_types {
+  typedef ldpc_code code_t;
+  typedef noisy_channel channel_t;
+  typedef bsc_channel bsc_t;
+  typedef biawgn_channel awgn_t;
+  typedef ldpc_decoder_gpu_static_parameters static_params_t;
+  typedef ldpc_decoder_gpu_dynamic_parameters dynamic_params_t;
+  typedef test_report report_t;
+  typedef error error_t;
+  static const int bsc_id = int(bsc), awgn_id = int(awgn);
 };
+typedef ldpc_b200_dropin::decoder<mirror_types> ldpc_decoder_gpu;
 
 // the CUDA-flavoured name the reference's main.cpp instantiates under CUDA_DECODER (main.cpp:315-319)
 typedef ldpc_decoder_gpu ldpc_decoder_gpu_cuda;

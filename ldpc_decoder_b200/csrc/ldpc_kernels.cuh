@@ -20,6 +20,7 @@
 // flood_permute_vecs (:225-275) has no equivalent: slots are indirect, frames never move.
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 #include <type_traits>
 #include <cuda_fp16.h>
@@ -33,6 +34,9 @@ namespace dev {
 #endif
 #ifndef LDPC_HMIN_CLAMP
 #define LDPC_HMIN_CLAMP 1 // fp16 table index: packed-half clamp + byte offsets (A/B on B200: CN +2.4 %, VN +5.1 %)
+#endif
+#ifndef LDPC_MERGE_DECISION_STORES
+#define LDPC_MERGE_DECISION_STORES 1 // variable-node pass with decisions: one 32-bit store per 32 slots (see vn_update_kernel)
 #endif
 constexpr int kThreads = LDPC_THREADS; // CTA size of the streaming kernels
 // Rows of degree <= D are held in registers (one read, one write per message); D is a template parameter chosen
@@ -262,10 +266,19 @@ __device__ __forceinline__ const uint16_t *stage_phi_table(const uint16_t *g_tab
 }
 
 // control block handed to the streaming kernels: ctl[0] = done flag, ctl[1] = log2 of the active vectors per row
-// (0 = all of them)
+// (0 = all of them), ctl[4] = "this period's refill is fused into its first check-node pass" (SchedState::fused_now)
 __device__ __forceinline__ uint32_t active_log2(const uint32_t *ctl, uint32_t log2_g) {
   const uint32_t a = ctl ? ctl[1] : 0u;
   return a ? a : log2_g;
+}
+// Fused refill is chosen per check period ON THE DEVICE (the scheduler knows how many frames it loads): the host
+// enqueues both variants of the refill and of the period's first check-node pass, and the variant that was not chosen
+// exits at its first instruction.  gate: 0 = always run, 1 = run only in a fused period, 2 = only in a plain period.
+enum : uint32_t { kGateNone = 0, kGateFused = 1, kGatePlain = 2 };
+constexpr int kCtlFused = 4;
+__device__ __forceinline__ bool gated_off(const uint32_t *ctl, uint32_t gate) {
+  if (gate == kGateNone || !ctl) return false;
+  return (ctl[kCtlFused] != 0u) != (gate == kGateFused);
 }
 
 __device__ __forceinline__ uint32_t &word(uint4 &v, int i) { return reinterpret_cast<uint32_t *>(&v)[i]; }
@@ -352,8 +365,9 @@ template <class Tr, int kMaxRegDeg, bool kRefill, class Idx>
 __device__ __forceinline__ void
 cn_update_body(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
                const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
-               const uint32_t *__restrict__ done, const CnRefillArgs ra) {
+               const uint32_t *__restrict__ done, const CnRefillArgs ra, uint32_t gate) {
   if (done && *done) return; // the device-side scheduler has retired every frame: run-ahead launches are no-ops
+  if (gated_off(done, gate)) return;
   constexpr uint32_t kFull = (1u << Tr::kFramesPerVec) - 1u;
   const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
   const uint32_t G = 1u << log2_g; // row stride in vectors
@@ -476,8 +490,9 @@ template <class Tr, int kMaxRegDeg, class Idx>
 __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMaxRegDeg) * kThreads / cn_threads_for(kMaxRegDeg))
     cn_update_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
                      const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
-                     const uint32_t *__restrict__ done) {
-  cn_update_body<Tr, kMaxRegDeg, false, Idx>(msg, row_ptr, syn, phi_table, tab_last, n_checks, log2_g, done, CnRefillArgs{});
+                     const uint32_t *__restrict__ done, uint32_t gate) {
+  cn_update_body<Tr, kMaxRegDeg, false, Idx>(msg, row_ptr, syn, phi_table, tab_last, n_checks, log2_g, done, CnRefillArgs{},
+                                             gate);
 }
 
 // first check-node pass after a refill (one launch per check period): message and prior vectors of a row are both in
@@ -487,12 +502,13 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
 #ifndef LDPC_CN_REFILL_MINBLOCKS
 #define LDPC_CN_REFILL_MINBLOCKS 2
 #endif
-template <class Tr, int kMaxRegDeg>
+template <class Tr, int kMaxRegDeg, class Idx>
 __global__ void __launch_bounds__(kThreads, LDPC_CN_REFILL_MINBLOCKS)
     cn_update_refill_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr,
                             const uint8_t *__restrict__ syn, const uint16_t *__restrict__ phi_table, uint32_t tab_last,
-                            uint32_t n_checks, uint32_t log2_g, const uint32_t *__restrict__ done, const CnRefillArgs ra) {
-  cn_update_body<Tr, kMaxRegDeg, true, size_t>(msg, row_ptr, syn, phi_table, tab_last, n_checks, log2_g, done, ra);
+                            uint32_t n_checks, uint32_t log2_g, const uint32_t *__restrict__ done, const CnRefillArgs ra,
+                            uint32_t gate) {
+  cn_update_body<Tr, kMaxRegDeg, true, Idx>(msg, row_ptr, syn, phi_table, tab_last, n_checks, log2_g, done, ra, gate);
 }
 
 // ---------------------------------------------------------------- check-node pass, long rows (high-rate codes)
@@ -507,8 +523,9 @@ template <class Tr, int kParts>
 __global__ void __launch_bounds__(kThreads, 3)
     cn_update_split_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr,
                            const uint8_t *__restrict__ syn, const uint16_t *__restrict__ phi_table, uint32_t tab_last,
-                           uint32_t n_checks, uint32_t log2_g, const uint32_t *__restrict__ done) {
+                           uint32_t n_checks, uint32_t log2_g, const uint32_t *__restrict__ done, uint32_t gate) {
   if (done && *done) return;
+  if (gated_off(done, gate)) return;
   constexpr int kChunk = 8;
   constexpr int kVecPerWarp = 32 / kParts;
   const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last);
@@ -618,8 +635,9 @@ template <class Tr, int kMaxRegDeg>
 __global__ void __launch_bounds__(kBulkTileVec, 2)
     cn_update_bulk_kernel(uint4 *__restrict__ msg, const uint32_t *__restrict__ row_ptr, const uint8_t *__restrict__ syn,
                           const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_checks, uint32_t log2_g,
-                          const uint32_t *__restrict__ done) {
+                          const uint32_t *__restrict__ done, uint32_t gate) {
   if (done && *done) return;
+  if (gated_off(done, gate)) return;
   extern __shared__ __align__(16) uint16_t s_table[]; // [table | stages | barriers]
   const uint32_t table_bytes = Tr::kUsesTable ? (tab_last / 8 + 1) * 16 : 0;
   uint4 *stages = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(s_table) + table_bytes);
@@ -699,10 +717,38 @@ __global__ void __launch_bounds__(kBulkTileVec, 2)
 // ---------------------------------------------------------------- variable-node pass
 // One thread = (variable v, frame vector g).  T = llr0 + sum of incoming c2v in CSC order; every edge gets
 // phi(T - m_e); optionally the hard decision signbit(T)==0 is written bit-sliced (flood.cu:117-189).
-// The gather list of the thread's NEXT item is fetched while the current messages are in flight.
+//
+// Gather list: the reference reads in_bit_to_edge[v], then in_to_out_edge[...] (two DEPENDENT index loads,
+// flood.cu:131-137).  Under a saturated memory system each of them is a long L2 round trip that a warp sits through
+// with nothing else in flight (ncu, profiles/r05: more stall samples on the two index loads than on the message loads
+// themselves).  Here the list is a padded row per variable ("ELL"): VnEll::kWords u32 = [degree, row of edge 0..D-1,
+// ..., first CSC edge], ONE independent load level, fetched for the thread's NEXT item right after the current item's
+// message loads are issued, so it arrives with them.  A degree above kMaxRegDeg marks a long variable: its list is
+// read from col_ptr / in_to_out (the last word = col_ptr[v]).
+template <int kMaxRegDeg> struct VnEll {
+  static constexpr int kWords = kMaxRegDeg <= 6 ? 8 : 12;
+};
+
+template <int kMaxRegDeg>
+__device__ __forceinline__ void vn_fetch_list(const uint32_t *__restrict__ vn_ell, uint32_t v, uint32_t &deg,
+                                              uint32_t &first_edge, uint32_t (&rows)[kMaxRegDeg]) {
+  constexpr int W = VnEll<kMaxRegDeg>::kWords;
+  const uint4 *e = reinterpret_cast<const uint4 *>(vn_ell) + size_t(v) * (W / 4);
+  uint32_t w[W];
+#pragma unroll
+  for (int q = 0; q < W / 4; ++q) {
+    const uint4 x = __ldg(e + q);
+    w[4 * q] = x.x, w[4 * q + 1] = x.y, w[4 * q + 2] = x.z, w[4 * q + 3] = x.w;
+  }
+  deg = w[0];
+  first_edge = w[W - 1];
+#pragma unroll
+  for (int k = 0; k < kMaxRegDeg; ++k) rows[k] = w[1 + k];
+}
+
 template <class Tr, bool kFinalBits, int kMaxRegDeg, class Idx>
 __global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMaxRegDeg) * kThreads / vn_threads_for(kMaxRegDeg))
-    vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ col_ptr,
+    vn_update_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ vn_ell,
                      const uint32_t *__restrict__ in_to_out, uint8_t *__restrict__ hard,
                      const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_vars, uint32_t log2_g,
                      const uint32_t *__restrict__ done) {
@@ -717,35 +763,16 @@ __global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMa
   uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   uint32_t a_next = 0, deg_next = 0;
   uint32_t rows_next[kMaxRegDeg];
-  if (Tr::kPrefetchVN && item < total) {
-    const uint32_t v = uint32_t(item >> log2_ga);
-    a_next = __ldg(col_ptr + v);
-    deg_next = __ldg(col_ptr + v + 1) - a_next;
-#pragma unroll
-    for (int k = 0; k < kMaxRegDeg; ++k)
-      if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
-  }
+  if (Tr::kPrefetchVN && item < total) vn_fetch_list<kMaxRegDeg>(vn_ell, uint32_t(item >> log2_ga), deg_next, a_next, rows_next);
   for (; item < total; item += stride) {
     const uint32_t v = uint32_t(item >> log2_ga);
     const uint32_t g = uint32_t(item) & (GA - 1u);
-    if (!Tr::kPrefetchVN) {
-      a_next = __ldg(col_ptr + v);
-      deg_next = __ldg(col_ptr + v + 1) - a_next;
-#pragma unroll
-      for (int k = 0; k < kMaxRegDeg; ++k)
-        if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
-    }
+    if (!Tr::kPrefetchVN) vn_fetch_list<kMaxRegDeg>(vn_ell, v, deg_next, a_next, rows_next);
     const uint32_t a = a_next, deg = deg_next;
     uint4 T = ld_stream(llr0 + ((Idx(v) << log2_g) + g));
     if (deg <= kMaxRegDeg) {
-      if (deg == 0 && Tr::kPrefetchVN && item + stride < total) { // isolated variable: still fetch the next item
-        const uint32_t vn = uint32_t((item + stride) >> log2_ga);
-        a_next = __ldg(col_ptr + vn);
-        deg_next = __ldg(col_ptr + vn + 1) - a_next;
-#pragma unroll
-        for (int k = 0; k < kMaxRegDeg; ++k)
-          if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
-      }
+      if (deg == 0 && Tr::kPrefetchVN && item + stride < total) // isolated variable: still fetch the next item
+        vn_fetch_list<kMaxRegDeg>(vn_ell, uint32_t((item + stride) >> log2_ga), deg_next, a_next, rows_next);
       DegDispatch<kMaxRegDeg>::run(deg, [&](auto deg_c) {
         constexpr int DEG = decltype(deg_c)::value;
         uint4 m[DEG];
@@ -755,14 +782,8 @@ __global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMa
           at[k] = (Idx(rows_next[k]) << log2_g) + g;
           m[k] = ld_stream(msg + at[k]);
         }
-        if (Tr::kPrefetchVN && item + stride < total) { // next item's gather list behind the message loads
-          const uint32_t vn = uint32_t((item + stride) >> log2_ga);
-          a_next = __ldg(col_ptr + vn);
-          deg_next = __ldg(col_ptr + vn + 1) - a_next;
-#pragma unroll
-          for (int k = 0; k < kMaxRegDeg; ++k)
-            if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
-        }
+        if (Tr::kPrefetchVN && item + stride < total) // next item's gather list behind the message loads
+          vn_fetch_list<kMaxRegDeg>(vn_ell, uint32_t((item + stride) >> log2_ga), deg_next, a_next, rows_next);
 #pragma unroll
         for (int k = 0; k < DEG; ++k) {
 #pragma unroll
@@ -775,14 +796,8 @@ __global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMa
         }
       });
     } else {
-      if (Tr::kPrefetchVN && item + stride < total) {
-        const uint32_t vn = uint32_t((item + stride) >> log2_ga);
-        a_next = __ldg(col_ptr + vn);
-        deg_next = __ldg(col_ptr + vn + 1) - a_next;
-#pragma unroll
-        for (int k = 0; k < kMaxRegDeg; ++k)
-          if (k < deg_next) rows_next[k] = __ldg(in_to_out + a_next + k);
-      }
+      if (Tr::kPrefetchVN && item + stride < total)
+        vn_fetch_list<kMaxRegDeg>(vn_ell, uint32_t((item + stride) >> log2_ga), deg_next, a_next, rows_next);
       for (uint32_t k = 0; k < deg; ++k) {
         const uint4 mk = ld_cached(msg + ((Idx(__ldg(in_to_out + a + k)) << log2_g) + g));
 #pragma unroll
@@ -800,6 +815,20 @@ __global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMa
 #pragma unroll
       for (int w = 0; w < 4; ++w) bits |= Tr::hard_bits(word(T, w)) << (w * Tr::kFramesPerWord);
       uint8_t *row = hard + size_t(v) * hard_row_bytes;
+#if LDPC_MERGE_DECISION_STORES
+      // The lanes of 32 consecutive slots (4 threads in fp16, 8 in fp32: always the same variable, a row holds at least
+      // 32 slots) merge their decision bits into ONE 32-bit store with shuffles instead of four one-byte stores.
+      if (Tr::kFramesPerVec == 8) {
+        uint32_t b = bits | (__shfl_down_sync(0xFFFFFFFFu, bits, 1) << 8);
+        b |= __shfl_down_sync(0xFFFFFFFFu, b, 2) << 16;
+        if ((g & 3u) == 0) *reinterpret_cast<uint32_t *>(row + g) = b;
+      } else {
+        uint32_t b = bits | (__shfl_down_sync(0xFFFFFFFFu, bits, 1) << 4);
+        b |= __shfl_down_sync(0xFFFFFFFFu, b, 2) << 8;
+        b |= __shfl_down_sync(0xFFFFFFFFu, b, 4) << 16;
+        if ((g & 7u) == 0) *reinterpret_cast<uint32_t *>(row + (g >> 1)) = b;
+      }
+#else
       if (Tr::kFramesPerVec == 8) {
         row[g] = uint8_t(bits);
       } else {
@@ -807,6 +836,7 @@ __global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMa
         const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, bits, 1);
         if ((g & 1u) == 0) row[g >> 1] = uint8_t(bits | (other << 4));
       }
+#endif
     }
   }
 }
@@ -854,16 +884,23 @@ struct RefillEntry {     // one new frame
 // addresses of its new lanes are looked up once, not once per variable.
 // kMsgRows = false (decode(), fused path): only the priors are written here; the first check-node pass of the period
 // (cn_update_refill_kernel) derives the start messages from them.
-template <class Tr, bool kPacked, bool kMsgRows>
+// kSrc: what the source array holds -- kSrcNative: llr elements of the decoder's precision; kSrcPackedBits: one bit
+// per transmitted variable (extension f3); kSrcHalf (fp32 decoders only): IEEE halves, widened here -- "fp16 transfer
+// with fp32 compute", the split the reference leaves open (h/common.h:35-37 sets transfer_llr_t = llr_t "for
+// simplicity"): half the H2D bytes of the fp32 path, arithmetic unchanged.
+enum : int { kSrcNative = 0, kSrcPackedBits = 1, kSrcHalf = 2 };
+template <class Tr, int kSrc, bool kMsgRows>
 __global__ void __launch_bounds__(kThreads)
     refill_kernel(uint4 *__restrict__ msg, uint4 *__restrict__ llr0, const void *__restrict__ src,
                   const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
                   const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
                   const uint32_t *__restrict__ col_ptr, const uint32_t *__restrict__ in_to_out,
                   const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t n_regular, uint32_t log2_g,
-                  int channel, float param) {
-  constexpr bool packed_bits = kPacked;
+                  int channel, float param, const uint32_t *__restrict__ ctl, uint32_t gate) {
+  constexpr bool packed_bits = kSrc == kSrcPackedBits;
+  static_assert(kSrc != kSrcHalf || Tr::kFramesPerVec == 4, "half transfer elements are widened by fp32 decoders only");
   if (*n_new_ptr == 0) return; // written by the scheduler kernel (or the host for kernel-level calls)
+  if (gated_off(ctl, gate)) return;
   constexpr int V = Tr::kFramesPerVec;
   constexpr uint32_t kFull = (1u << V) - 1u;
   const uint32_t G = 1u << log2_g;
@@ -898,9 +935,12 @@ __global__ void __launch_bounds__(kThreads)
           uint32_t pbit = 0;
           if (packed_bits) pbit = (__ldg(static_cast<const uint32_t *>(src) + off[j] + (i >> 5)) >> (i & 31u)) & 1u;
           if (V == 4) {
-            word(L, j & 3) = TraitsF32::to_llr(packed_bits ? (pbit ? 0x3F800000u : 0xBF800000u)
-                                                           : __ldg(static_cast<const uint32_t *>(src) + off[j] + at_i),
-                                               channel, param);
+            uint32_t raw;
+            if (packed_bits) raw = pbit ? 0x3F800000u : 0xBF800000u;
+            else if (kSrc == kSrcHalf)
+              raw = __float_as_uint(__half2float(__ushort_as_half(__ldg(static_cast<const uint16_t *>(src) + off[j] + at_i))));
+            else raw = __ldg(static_cast<const uint32_t *>(src) + off[j] + at_i);
+            word(L, j & 3) = TraitsF32::to_llr(raw, channel, param);
           } else {
             const uint32_t raw = TraitsF16::to_llr(packed_bits ? uint16_t(pbit ? 0x3C00u : 0xBC00u)
                                                                : __ldg(static_cast<const uint16_t *>(src) + off[j] + at_i),
@@ -1050,16 +1090,22 @@ struct SchedConst {
   uint64_t frame_stride;
   // LDPC_B200_FLAG_EARLY_RETIRE: once the input is exhausted, retire frames as soon as they stop and compact the
   // survivors into the low slots so that the flood kernels touch only 2^log2_ga vectors per row
-  uint32_t early_retire, log2_v /* log2 frames per 16-byte vector */, min_log2_p_active, pad2;
+  uint32_t early_retire, log2_v /* log2 frames per 16-byte vector */, min_log2_p_active;
+  // a period that loads at least this many frames fuses its refill into its first check-node pass (0xFFFFFFFF: never)
+  uint32_t fused_min_new;
 };
 struct SchedState {
   uint32_t next_to_load, g;
   uint32_t done, log2_ga; // control block read by the streaming kernels (ctl[0], ctl[1]): keep adjacent
   uint32_t period, batch_active;
+  uint32_t fused_now, pad; // ctl[kCtlFused]: the refill of this period is fused into its first check-node pass
 };
+static_assert(offsetof(SchedState, fused_now) - offsetof(SchedState, done) == 4 * kCtlFused, "control block layout");
 struct SchedSummary {
   uint32_t n_new, n_retired, next_to_load, done, g, n_stop, period, n_moves;
-  uint32_t log2_p_active, pad[3]; // slots the flood kernels process from now on
+  uint32_t log2_p_active; // slots the flood kernels process from now on
+  uint32_t fused;         // this period's refill is fused into the next check-node pass
+  uint32_t pad[2];
 };
 struct SlotMove {
   uint32_t src, dst;
@@ -1140,6 +1186,8 @@ __global__ void __launch_bounds__(kSchedThreads)
     st->log2_ga = 0; // all vectors of a row are live
     st->period = 0;
     st->batch_active = c.batch;
+    st->fused_now = c.batch >= c.fused_min_new ? 1u : 0u;
+    st->pad = 0;
     *n_new_out = c.batch;
   }
 }
@@ -1160,9 +1208,10 @@ __global__ void __launch_bounds__(kSchedThreads)
     for (uint32_t w = tid; w < PW; w += blockDim.x) new_mask[w] = retire_mask[w] = 0;
     if (tid == 0) {
       *n_new_out = 0;
-      SchedSummary sm = {0, 0, st->next_to_load, 1, st->g, 0, st->period, 0, c.log2_p, {0, 0, 0}};
+      SchedSummary sm = {0, 0, st->next_to_load, 1, st->g, 0, st->period, 0, c.log2_p, 0, {0, 0}};
       *summary = sm;
       st->period++;
+      st->fused_now = 0;
     }
     return;
   }
@@ -1266,8 +1315,9 @@ __global__ void __launch_bounds__(kSchedThreads)
       if (Bn > 0 && log2_pn < cur_log2_p) st->log2_ga = log2_pn - c.log2_v;
       st->batch_active = Bn;
       st->period = period + 1;
+      st->fused_now = 0;
       SchedSummary sm = {0, tot_stop, next, Bn == 0 ? 1u : 0u, g, tot_stop, period, n_moves,
-                         (Bn > 0 && log2_pn < cur_log2_p) ? log2_pn : cur_log2_p, {0, 0, 0}};
+                         (Bn > 0 && log2_pn < cur_log2_p) ? log2_pn : cur_log2_p, 0, {0, 0}};
       *summary = sm;
     }
     return;
@@ -1335,8 +1385,10 @@ __global__ void __launch_bounds__(kSchedThreads)
     st->g = g + c.k_check;
     st->done = all_done ? 1u : 0u;
     st->period = period + 1;
+    const uint32_t fused = (n_new > 0 && n_new >= c.fused_min_new) ? 1u : 0u;
+    st->fused_now = fused;
     SchedSummary sm = {n_new, all_done ? B : n_new, next + n_new, all_done ? 1u : 0u, g, n_stop, period, 0,
-                       c.log2_p, {0, 0, 0}};
+                       c.log2_p, fused, {0, 0}};
     *summary = sm;
   }
 }

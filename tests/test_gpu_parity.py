@@ -17,6 +17,22 @@ RTOL_MSG = 1e-3   # north_star tolerance for fp32 messages
 ATOL_MSG = 1e-6   # absolute floor: flushed-to-zero tails of 2e^-x (ex2.approx.ftz) vs denormals in libm
 
 
+def _require_ref(*precisions):
+    """The unmodified reference build (oracle/_ref/libldpc_ref_*.so) is part of the parity evidence: it is compiled by
+    __graft_entry__.build() wherever /root/reference exists and travels to the GPU box with the snapshot, so a GPU test
+    that does not find it FAILS (it used to skip, which would have hidden a missing library behind a green run).
+    LDPC_B200_ALLOW_MISSING_REF=1 turns the failure back into a skip for boxes that never had the reference tree."""
+    import os
+
+    missing = [p for p in precisions if not rb.available(p)]
+    if not missing:
+        return
+    msg = f"oracle/_ref reference library not built for {missing}: run `python -c 'import __graft_entry__ as g; g.build()'`"
+    if os.environ.get("LDPC_B200_ALLOW_MISSING_REF") == "1" and not os.path.isdir("/root/reference/src"):
+        pytest.skip(msg)
+    pytest.fail(msg)
+
+
 def _frames(gen, n, channel, noise, seed, dtype):
     inp, syn, bits = harness.make_frames(gen, n, channel, noise, seed=seed, dtype=dtype)
     return inp, syn, bits, harness.channel_param(channel, noise)
@@ -46,9 +62,16 @@ def test_phi_abs_fp32_matches_oracle():
     assert np.percentile(rel[big], 99) < 5e-6
 
 
+@pytest.mark.parametrize("idx64", [False, True], ids=["idx32", "idx64"])
 @pytest.mark.parametrize("name", ["reg36", "readme13", "hideg", "tiny"])
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
-def test_kernel_steps_match_oracle(small_codes, name, prec):
+def test_kernel_steps_match_oracle(small_codes, name, prec, idx64, monkeypatch):
+    """idx64: the kernels instantiated with 64-bit vector indices (Idx = size_t), which the library only picks by
+    itself when max(E, N) * vectors per row >= 2^32 (N = 2^22 at 2^13 slots); LDPC_B200_IDX64=1 forces them."""
+    if idx64:
+        monkeypatch.setenv("LDPC_B200_IDX64", "1")
+    else:
+        monkeypatch.delenv("LDPC_B200_IDX64", raising=False)
     gen, path = small_codes[name]
     code = L.Code(path=path)
     o = ob.OracleCode(path=path)
@@ -100,8 +123,7 @@ def test_kernel_steps_match_oracle(small_codes, name, prec):
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
 def test_phi_table_and_refill_match_reference_build(small_codes, prec, tmp_path):
     """The reference's own flood_refill writes phi(llr) on every edge: feed it every half / a float sweep."""
-    if not rb.available(prec):
-        pytest.skip("oracle/_ref reference library not built")
+    _require_ref(prec)
     from ldpc_decoder_b200 import alist
 
     gen = alist.make_regular_code(32768, 3, 6, seed=2)
@@ -146,8 +168,7 @@ def test_phi_table_and_refill_match_reference_build(small_codes, prec, tmp_path)
 @pytest.mark.parametrize("name", ["reg36", "readme13", "hideg"])
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
 def test_iterations_match_reference_build(small_codes, name, prec):
-    if not rb.available(prec):
-        pytest.skip("oracle/_ref reference library not built")
+    _require_ref(prec)
     gen, path = small_codes[name]
     fp16 = prec == "fp16"
     dt = np.float16 if fp16 else np.float32
@@ -237,11 +258,15 @@ def test_decode_matches_oracle(small_codes, prec, name, channel, noise, n_frames
     assert np.array_equal(gen.syndrome_packed(res[conv]), syn[conv])
 
 
+@pytest.mark.parametrize("idx64", [False, True], ids=["idx32", "idx64"])
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
 @pytest.mark.parametrize("name,noise,n_frames,log2p", [("reg36", 0.78, 96, 5), ("readme13", 0.55, 48, 4)])
-def test_decode_matches_reference_build(small_codes, prec, name, noise, n_frames, log2p):
-    if not rb.available(prec):
-        pytest.skip("oracle/_ref reference library not built")
+def test_decode_matches_reference_build(small_codes, prec, name, noise, n_frames, log2p, idx64, monkeypatch):
+    _require_ref(prec)
+    if idx64:  # 64-bit-index instantiations of every flood kernel, incl. the fused check-node pass
+        monkeypatch.setenv("LDPC_B200_IDX64", "1")
+    else:
+        monkeypatch.delenv("LDPC_B200_IDX64", raising=False)
     gen, path = small_codes[name]
     dec, inp, syn, bits, prm, res, iters, rep = _decode_case(gen, path, prec, "awgn", noise, n_frames, log2p, 60, 10, 9)
     ref = rb.RefDecoder(path, "awgn", noise, log2p, prec)
@@ -336,8 +361,7 @@ def test_config0_full_size_matches_reference_build(tmp_path):
     """configs[0] shape: README-shaped N = 2^20 code, AWGN, `-p 8 -m 2 -i 120` (256 in flight, 512 frames, check
     every 10).  fp16 build of the reference vs this decoder on identical inputs: decisions bit-exact, same
     iteration statistics."""
-    if not rb.available("fp16"):
-        pytest.skip("oracle/_ref reference library not built")
+    _require_ref("fp16")
     from ldpc_decoder_b200 import alist
 
     gen = alist.make_readme_shaped_code(20, seed=1)
@@ -357,41 +381,166 @@ def test_config0_full_size_matches_reference_build(tmp_path):
     assert harness.count_bit_errors(res, bits).sum() == 0
 
 
-def test_config1_shape_bsc_high_rate_fp32():
-    """configs[1] shape: rate-0.9 code on a BSC, fp32 messages, 2^10 frames in flight.  Stand-in: (3,32)-regular,
-    N = 2^20 (check degree 32 exercises the long-row path).  Property: decoded words satisfy their syndromes and
-    equal the transmitted words."""
+def _synth(dec, channel, noise, start, n, gen, fp16):
+    """n frames of the reference harness' streams generated on the device (row f2) -> CUDA tensors + transmitted words."""
+    import torch
+
+    N, M = gen.n_vars, gen.n_checks
+    d_in = torch.zeros((N, n), dtype=torch.float16 if fp16 else torch.float32, device="cuda")
+    d_syn = torch.zeros((n, (M + 31) // 32), dtype=torch.int32, device="cuda")
+    d_ref = torch.zeros((n, N // 32), dtype=torch.int32, device="cuda")
+    dec.synthesize_frames(L.BSC if channel == "bsc" else L.AWGN, noise, start, n, d_in, d_syn, d_ref)
+    return d_in, d_syn, d_ref
+
+
+def _compare_with_reference_build(gen, path, prec, channel, noise, log2p, n_frames, imax):
+    """decode() of this library and of the reference's own sm_100 build on the SAME host arrays, at the largest number
+    of frames in flight the reference's 32-bit indices allow (P * E < 2^32, flood.cu:98,137).  fp16: decisions and
+    per-run iteration statistics bit-exact; fp32: iteration counts equal on >= 97 % of frames (this decoder against
+    itself is deterministic; against the reference's libm phi a frame can sit on a decision boundary), decisions
+    bit-exact on every frame both converge, and equal to the transmitted words."""
+    import torch
+
+    fp16 = prec == "fp16"
+    assert (gen.n_edges << log2p) < 2 ** 32
+    dec = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, log2p)
+    assert dec.parallel_factor() == 1 << log2p
+    nz = float(np.float16(noise)) if (fp16 and channel == "awgn") else noise
+    d_in, d_syn, d_ref = _synth(dec, channel, nz, 77, n_frames, gen, fp16)
+    inp, syn, ref_bits = d_in.cpu().numpy(), d_syn.cpu().numpy().view(np.uint32), d_ref.cpu().numpy().view(np.uint32)
+    del d_in, d_syn, d_ref
+    torch.cuda.empty_cache()
+    prm = harness.channel_param(channel, nz)
+    res, iters, rep = dec.decode(L.BSC if channel == "bsc" else L.AWGN, prm, inp, syn, num_iter_max=imax)
+    del dec
+    ref = rb.RefDecoder(path, channel, nz, log2p, prec)
+    assert ref.P == 1 << log2p
+    assert ref.channel_param() == pytest.approx(prm, rel=1e-6)
+    rres, rrep = ref.decode(inp, syn, imax, 10)
+    ref.close()
+    conv = iters < imax
+    assert conv.mean() > 0.9, conv.mean()
+    assert np.array_equal(res[conv], ref_bits[conv])
+    if fp16:
+        assert np.array_equal(res, rres)
+        assert (rep["max_iter"], rep["min_iter"]) == (rrep["max_iter"], rrep["min_iter"])
+        assert rep["avg_iter"] == pytest.approx(rrep["avg_iter"], rel=1e-6)
+    else:
+        same = (res == rres).all(axis=1)
+        assert same[conv].mean() >= 0.97, same[conv].mean()
+        rconv = (rres == ref_bits).all(axis=1)           # the reference decoded these frames too
+        both = conv & rconv
+        assert both.mean() > 0.9
+        assert np.array_equal(res[both], rres[both])
+        assert abs(rep["avg_iter"] - rrep["avg_iter"]) <= 0.25
+        assert abs(int(rep["max_iter"]) - int(rrep["max_iter"])) <= 10 and rep["min_iter"] == rrep["min_iter"]
+    return rep, rrep
+
+
+def test_config1_full_size_matches_reference_build(tmp_path):
+    """configs[1] shape at full size: rate-0.9 code on a BSC, fp32 messages, 2^10 frames in flight (stand-in:
+    (3,32)-regular, N = 2^20: check degree 32 runs the split-row check-node kernel).  The reference can index this
+    (P * E = 3.2e9 < 2^32), so it is compared frame by frame instead of through properties."""
+    _require_ref("fp32")
     from ldpc_decoder_b200 import alist
 
     gen = alist.make_regular_code(1 << 20, 3, 32, seed=4)
-    dec = L.Decoder(L.Code.from_generated(gen), L.FP32, 10)
-    assert dec.parallel_factor() == 1024
-    inp, syn, bits, prm = _frames(gen, 96, "bsc", 0.004, 3, np.float32)
-    res, iters, rep = dec.decode(L.BSC, prm, inp, syn, num_iter_max=100, pool_frames=96, n_frames=2048)
-    conv = iters < 100
-    assert conv.mean() > 0.9, conv.mean()
-    idx = np.arange(2048) % 96
-    assert np.array_equal(gen.syndrome_packed(res[conv][:128]), syn[idx[conv][:128]])
-    assert np.array_equal(res[conv], bits[idx[conv]])
+    path = str(tmp_path / "bsc_rate09.alist")
+    alist.write_alist(gen, path)
+    _compare_with_reference_build(gen, path, "fp32", "bsc", 0.004, 10, 1024 + 192, 100)
 
 
 @pytest.mark.parametrize("prec", ["fp16", "fp32"])
-def test_config4_shape_regular36_n4m(prec):
-    """configs[4] shape: harness-generated regular (3,6) code, N = 2^22, AWGN just below threshold, up to 500
-    iterations (long-tail refill stress: frames in flight << frames)."""
+def test_config4_full_size_matches_reference_build(prec, tmp_path):
+    """configs[4] shape at full size: harness-generated regular (3,6) code, N = 2^22, AWGN just below threshold, up to
+    500 iterations, at the 2^8 frames in flight the reference can still index (P * E = 3.2e9)."""
+    _require_ref(prec)
     from ldpc_decoder_b200 import alist
 
     gen = alist.make_regular_code(1 << 22, 3, 6, seed=6)
-    dt = np.float16 if prec == "fp16" else np.float32
-    dec = L.Decoder(L.Code.from_generated(gen), L.FP16 if prec == "fp16" else L.FP32, 6)
-    inp, syn, bits, prm = _frames(gen, 32, "awgn", 0.86, 5, dt)
+    path = str(tmp_path / "reg36_n4m.alist")
+    alist.write_alist(gen, path)
+    rep, rrep = _compare_with_reference_build(gen, path, prec, "awgn", 0.86, 8, 256 + 96, 500)
+    assert rep["max_iter"] <= 500 + 10 + 1
+
+
+def test_config4_long_tail_refill_stress():
+    """configs[4] shape, frames in flight << frames (long-tail refill stress): decoded words equal the transmitted
+    words and satisfy their syndromes (size-independent properties; the frame-by-frame comparison is the test above)."""
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_regular_code(1 << 22, 3, 6, seed=6)
+    dec = L.Decoder(L.Code.from_generated(gen), L.FP16, 6)
+    inp, syn, bits, prm = _frames(gen, 32, "awgn", 0.86, 5, np.float16)
     res, iters, rep = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=500, pool_frames=32, n_frames=256)
     conv = iters < 500
     assert conv.mean() > 0.9, (conv.mean(), rep)
-    assert rep["max_iter"] <= 500 + 10 + 1
     idx = np.arange(256) % 32
     assert np.array_equal(res[conv], bits[idx[conv]])
     assert np.array_equal(gen.syndrome_packed(res[conv][:32]), syn[idx[conv][:32]])
+
+
+def test_config2_bench_size_is_transitively_equal_to_the_reference_build(tmp_path):
+    """configs[2] (the bench workload: N = 2^20 README-shaped code, fp16, 2^12 frames in flight) is beyond the
+    reference's 32-bit indices, so parity at that size is shown transitively on 8192 distinct frames of the bench's
+    noise level:  (A) this decoder at P = 2^12  ==  (B) this decoder at P = 2^8  on all 8192 frames, and
+    (C) this decoder at P = 2^8  ==  (D) the reference's own build at P = 2^8  on the first 512 of the same frames.
+    fp16 arithmetic is deterministic and frames never interact, so a frame's iteration count depends only on whether
+    it belongs to the first batch (counts k*j + 1, ldpc_decoder_gpu.cu:306-309) or was loaded later (k*j)."""
+    _require_ref("fp16")
+    import torch
+
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_readme_shaped_code(20, seed=1)
+    path = str(tmp_path / "readme20.alist")
+    alist.write_alist(gen, path)
+    code = L.Code(path=path)
+    sigma = float(np.float16(0.824))
+    prm = harness.channel_param("awgn", sigma)
+    n, imax, W = 8192, 120, gen.n_vars // 32
+    small = L.Decoder(code, L.FP16, 8)
+    d_in, d_syn, d_ref = _synth(small, "awgn", sigma, 0, n, gen, True)
+    ref_bits = d_ref.cpu().numpy().view(np.uint32)
+
+    def run(dec, n_frames):
+        d_res = torch.zeros((n_frames, W), dtype=torch.int32, device="cuda")
+        # frames 0..n_frames-1 are the first columns of the [N][8192] array: read them through the pool stride
+        _, it, rep = dec.decode(L.AWGN, prm, d_in, d_syn, n_frames=n_frames, num_iter_max=imax, results=d_res,
+                                pool_frames=n)
+        return d_res.cpu().numpy().view(np.uint32), it, rep
+
+    res_b, it_b, rep_b = run(small, n)
+    res_c, it_c, rep_c = run(small, 512)
+    del small
+    big = L.Decoder(code, L.FP16, 12)
+    assert big.parallel_factor() == 4096
+    res_a, it_a, rep_a = run(big, n)
+    del big
+    torch.cuda.empty_cache()
+    # (A) vs (B): same role in both runs for frames < 256 (first batch) and >= 4096 (loaded later)
+    same_role = np.r_[0:256, 4096:n]
+    assert np.array_equal(it_a[same_role], it_b[same_role])
+    mid = np.r_[256:4096]                                   # first batch at P = 2^12, loaded later at P = 2^8
+    assert np.all(np.abs(it_a[mid].astype(np.int64) - it_b[mid].astype(np.int64)) <= 11)
+    conv = (it_a < imax) & (it_b < imax)
+    assert conv.mean() > 0.95
+    assert np.array_equal(res_a[conv], res_b[conv]) and np.array_equal(res_a[conv], ref_bits[conv])
+    # (B) vs (C): the first 512 frames decode the same inside a longer queue
+    assert np.array_equal(it_b[:512], it_c)
+    cc = it_c < imax
+    assert np.array_equal(res_b[:512][cc], res_c[cc])
+    # (C) vs (D): the reference's own build, same host arrays
+    inp = d_in[:, :512].contiguous().cpu().numpy()
+    syn = d_syn[:512].cpu().numpy().view(np.uint32)
+    del d_in, d_syn, d_ref
+    torch.cuda.empty_cache()
+    ref = rb.RefDecoder(path, "awgn", sigma, 8, "fp16")
+    rres, rrep = ref.decode(inp, syn, imax, 10)
+    ref.close()
+    assert np.array_equal(res_c, rres)
+    assert (rep_c["max_iter"], rep_c["min_iter"]) == (rrep["max_iter"], rrep["min_iter"])
+    assert rep_c["avg_iter"] == pytest.approx(rrep["avg_iter"], rel=1e-6)
 
 
 def test_graph_replay_equals_plain_launches(small_codes):
@@ -412,8 +561,7 @@ def test_graph_replay_equals_plain_launches(small_codes):
 def test_fer_ber_and_iteration_statistics_match_reference_build():
     """north_star parity item 3: FER/BER and iteration statistics agree with the reference within 95 % CIs, at a
     noise level where a sizeable fraction of frames fails (scripts/fer_compare.py; profiles/r01_fer_compare.json)."""
-    if not (rb.available("fp32") and rb.available("fp16")):
-        pytest.skip("oracle/_ref reference library not built")
+    _require_ref("fp32", "fp16")
     import importlib.util
     import os
 
@@ -446,7 +594,9 @@ def test_cli_matches_the_reference_command_line_program(prec):
     ref_bin = os.path.join(ROOT, "oracle", "_ref", f"ref_ldpc_decoder_cuda_{prec}")
     new_bin = os.path.join(ROOT, "ldpc_decoder_b200", "ldpc_decoder_b200_cli")
     if not (os.path.exists(ref_bin) and os.path.exists(new_bin)):
-        pytest.skip("CLI binaries not built")
+        if os.environ.get("LDPC_B200_ALLOW_MISSING_REF") == "1" and not os.path.isdir("/root/reference/src"):
+            pytest.skip("CLI binaries not built")
+        pytest.fail("CLI binaries not built: run __graft_entry__.build()")
     spec = importlib.util.spec_from_file_location("cli_compare", os.path.join(ROOT, "scripts", "cli_compare.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -459,6 +609,59 @@ def test_cli_matches_the_reference_command_line_program(prec):
     if prec == "fp32":  # decisions can differ on frames that do not converge
         assert abs(int(r["fer_any"]) - int(n["fer_any"])) <= 2
         assert r["iters"].split("/")[:2] == n["iters"].split("/")[:2]
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_reference_main_cpp_builds_and_runs_against_the_dropin_header(prec):
+    """The reference's OWN src/main.cpp (+ its PRNG, channel, report, alist and transpose sources), compiled unchanged
+    with include/ of this repository first on the include path -- so `#include "ldpc_decoder_gpu.h"` /
+    `"ldpc_decoder_gpu_cuda.h"` (main.cpp:4-5) resolve to the drop-in class -- and linked with libldpc_b200.so instead
+    of the reference's decoder (oracle/Makefile refdropin).  Run next to the reference's own build of the same
+    main.cpp: identical description, error counts, FER and iteration statistics."""
+    import importlib.util
+    import os
+    import subprocess
+    import tempfile
+
+    from conftest import ROOT
+    from ldpc_decoder_b200 import alist
+
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", f"ref_ldpc_decoder_cuda_{prec}")
+    new_bin = os.path.join(ROOT, "oracle", "_ref", f"dropin_ldpc_decoder_{prec}")
+    if not (os.path.exists(ref_bin) and os.path.exists(new_bin)):
+        if os.environ.get("LDPC_B200_ALLOW_MISSING_REF") == "1" and not os.path.isdir("/root/reference/src"):
+            pytest.skip("reference main.cpp builds not present")
+        pytest.fail("oracle/_ref/{ref_ldpc_decoder_cuda,dropin_ldpc_decoder}_* not built: run __graft_entry__.build()")
+    spec = importlib.util.spec_from_file_location("cli_compare", os.path.join(ROOT, "scripts", "cli_compare.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gen = alist.make_readme_shaped_code(14, seed=1)
+    path = os.path.join(tempfile.mkdtemp(), "standin_14.alist")
+    alist.write_alist(gen, path)
+    args = ["-f", path, "-c", "1", "-n", "0.80", "-p", "5", "-m", "4", "-e", "15", "-i", "60", "-s", "1000", "-l", "2"]
+    rt = subprocess.run([ref_bin] + args, capture_output=True, text=True, timeout=600).stdout
+    nt = subprocess.run([new_bin] + args, capture_output=True, text=True, timeout=600).stdout
+    r, n = mod.summary(rt), mod.summary(nt)
+    assert r["frames"] == n["frames"] == "128", (rt[-2000:], nt[-2000:])
+    assert r["description"] == n["description"]
+    for k in ("errors", "ber", "max_err", "fer_target", "fer_any", "iters", "mbits"):
+        if prec == "fp16" or k == "mbits":
+            assert r[k] == n[k], (k, r[k], n[k])
+    if prec == "fp32":
+        assert abs(int(r["fer_any"]) - int(n["fer_any"])) <= 2
+        assert r["iters"].split("/")[:2] == n["iters"].split("/")[:2]
+    # -l 2: the drop-in honours p_log (per-step times of the schedule, ldpc_decoder_gpu.cu:528-601)
+    assert "Steps 5-7 (load new vectors)" in nt and "decoder: time =" in nt
+    # the BSC path of the same binaries (on a code without punctured variables: DESIGN.md, deliberate deviation 1)
+    path = os.path.join(os.path.dirname(path), "reg36_14.alist")
+    alist.write_alist(alist.make_regular_code(1 << 14, 3, 6, seed=2), path)
+    args = ["-f", path, "-c", "0", "-n", "0.05", "-p", "5", "-m", "2", "-i", "40"]
+    r = mod.summary(subprocess.run([ref_bin] + args, capture_output=True, text=True, timeout=600).stdout)
+    n = mod.summary(subprocess.run([new_bin] + args, capture_output=True, text=True, timeout=600).stdout)
+    assert r["description"] == n["description"] and r["frames"] == n["frames"]
+    if prec == "fp16":
+        for k in ("errors", "fer_any", "iters"):
+            assert r[k] == n[k], (k, r[k], n[k])
 
 
 def test_llr_input_erased_override_and_argument_checks(small_codes):
@@ -579,6 +782,38 @@ def test_packed_bit_input_equals_float_input(small_codes, prec):
     res3, iters3, _ = dec.decode(L.BSC, prm, d_packed, syn, n_frames=150, num_iter_max=60, layout=L.LAYOUT_PACKED_BITS)
     assert np.array_equal(res, res3) and np.array_equal(iters, iters3)
     assert harness.count_bit_errors(res, bits)[iters < 60].sum() == 0
+
+
+@pytest.mark.parametrize("layout", ["interleaved", "frame_major"])
+def test_half_transfer_with_fp32_compute(small_codes, layout):
+    """SURVEY row f3, third item ("fp16 transfer with fp32 compute"; the reference keeps transfer_llr_t = llr_t,
+    h/common.h:35-37): LDPC_B200_FLAG_HALF_INPUT feeds IEEE halves to an FP32 decoder, which widens them when a frame
+    is loaded.  Results equal the FP32 decode of the half-rounded inputs bit for bit, with half the input bytes."""
+    import torch
+
+    gen, path = small_codes["readme13"]
+    inp, syn, bits, prm = _frames(gen, 150, "awgn", 0.6, 17, np.float32)
+    half = inp.astype(np.float16)
+    rounded = half.astype(np.float32)
+    n_reg = gen.n_vars - gen.n_erased
+    dec = L.Decoder(L.Code(path=path), L.FP32, 5)
+    res, iters, rep = dec.decode(L.AWGN, prm, rounded, syn, num_iter_max=60)
+    if layout == "interleaved":
+        res2, iters2, rep2 = dec.decode(L.AWGN, prm, half, syn, num_iter_max=60, flags=L.FLAG_HALF_INPUT)
+    else:
+        fm = np.ascontiguousarray(half[:n_reg].T)
+        res2, iters2, rep2 = dec.decode(L.AWGN, prm, fm, syn, n_frames=150, num_iter_max=60, flags=L.FLAG_HALF_INPUT,
+                                        layout=L.LAYOUT_FRAME_MAJOR)
+    assert np.array_equal(res, res2) and np.array_equal(iters, iters2)
+    syn_bytes = syn.nbytes
+    assert rep2["h2d_bytes"] - syn_bytes <= (rep["h2d_bytes"] - syn_bytes) // 2 + 4096
+    assert harness.count_bit_errors(res2, bits)[iters2 < 60].sum() == 0
+    # device-resident halves, and the flag is refused by an FP16 decoder (it takes halves anyway)
+    d_half = torch.from_numpy(half.view(np.int16)).cuda()
+    res3, iters3, _ = dec.decode(L.AWGN, prm, d_half, syn, n_frames=150, num_iter_max=60, flags=L.FLAG_HALF_INPUT)
+    assert np.array_equal(res, res3) and np.array_equal(iters, iters3)
+    with pytest.raises(L.LdpcError):
+        L.Decoder(L.Code(path=path), L.FP16, 5).decode(L.AWGN, prm, half, syn, flags=L.FLAG_HALF_INPUT)
 
 
 @pytest.mark.parametrize("prec", ["fp16", "fp32"])
