@@ -111,7 +111,10 @@ typedef struct ldpc_b200_decode_params {
   uint32_t input_pool_frames;     /* 0: input holds n_frames frames.  k>0: input/syndromes hold k      *
                                    * frames and frame f reads column f % k (benchmark recycling pool)  */
   uint32_t flags;                 /* LDPC_B200_FLAG_*                                                  */
-  uint32_t reserved[4];
+  uint32_t queue_lookahead_frames; /* ldpc_b200_decode_from_queue / _multi: frames a decoder keeps reserved   *
+                                   * beyond those it has loaded; 0 -> its frames in flight (every check can   *
+                                   * then load as many frames as it frees, as in a classic call)              */
+  uint32_t reserved[3];
 } ldpc_b200_decode_params;
 
 enum {
@@ -160,6 +163,7 @@ typedef struct ldpc_b200_report {
    * cn_s so that cn_s / (cn_launches - cn_refill_launches) is the plain check-node pass.                           */
   uint64_t cn_refill_launches;
   double cn_refill_s;
+  uint64_t frames_decoded; /* frames this call decoded (n_frames; less for a decoder sharing a queue with others) */
 } ldpc_b200_report;
 
 /* decode() (ldpc_decoder_gpu.h:102-110; semantics of ldpc_decoder_gpu.cu:283-634).
@@ -171,6 +175,35 @@ typedef struct ldpc_b200_report {
 ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *dec, const ldpc_b200_decode_params *params, uint32_t n_frames,
                                   const void *input, const uint32_t *syndromes, uint32_t *results,
                                   ldpc_b200_report *report, uint32_t *iter_counts);
+
+/* ---- one frame queue, several GPUs --------------------------------------------------------------
+ * The reference drives device 0 only (h/cuda_manager.h:52).  Frames are independent, so several decoders -- one per
+ * GPU -- can work through ONE queue of frames: a queue is an atomic cursor over the rows of the caller's arrays; each
+ * decoder reserves whole blocks of `block_frames` consecutive frames as its slots free up and decodes them as one
+ * continuous call (the reference's schedule: first batch, frame replacement at every check, one tail at the end of the
+ * queue), writing results / iter_counts rows of exactly the frames it decoded.  No collective on the data path.
+ *   shm_name == NULL : queue private to this process (threads, one per decoder: ldpc_b200_decode_multi does that);
+ *   shm_name != NULL : POSIX shared-memory object shared by the processes of one host (one process per GPU): one
+ *                      process passes create = 1 (with the sizes), the others open it afterwards with create = 0. */
+typedef struct ldpc_b200_queue ldpc_b200_queue;
+ldpc_b200_status ldpc_b200_queue_create(const char *shm_name, int32_t create, uint32_t n_frames, uint32_t block_frames,
+                                        ldpc_b200_queue **out);
+void ldpc_b200_queue_destroy(ldpc_b200_queue *queue);
+uint32_t ldpc_b200_queue_size(const ldpc_b200_queue *queue);
+void ldpc_b200_queue_reset(ldpc_b200_queue *queue); /* cursor back to frame 0 (no decoder may be drawing from it) */
+/* Like ldpc_b200_decode, with input / syndromes / results / iter_counts sized for the WHOLE queue (or a pool, see
+ * input_pool_frames); only the rows of the frames this decoder took are read and written; report->frames_decoded
+ * says how many those were.  Call it concurrently, once per decoder. */
+ldpc_b200_status ldpc_b200_decode_from_queue(ldpc_b200_decoder *dec, const ldpc_b200_decode_params *params,
+                                             ldpc_b200_queue *queue, const void *input, const uint32_t *syndromes,
+                                             uint32_t *results, ldpc_b200_report *report, uint32_t *iter_counts);
+/* One process, n_decs decoders (one per device, same code and precision): a private queue over the n_frames frames, one
+ * host thread per decoder, a merged report (counters summed, longest elapsed / device time, iteration statistics over
+ * all frames) and optionally each decoder's own (per_decoder[n_decs], nullable).  block_frames = 0 picks a default. */
+ldpc_b200_status ldpc_b200_decode_multi(ldpc_b200_decoder *const *decs, uint32_t n_decs,
+                                        const ldpc_b200_decode_params *params, uint32_t n_frames, const void *input,
+                                        const uint32_t *syndromes, uint32_t *results, ldpc_b200_report *report,
+                                        ldpc_b200_report *per_decoder, uint32_t *iter_counts, uint32_t block_frames);
 
 /* ---- kernel-level entry points (parity tests and profiling; same kernels decode() runs) ------ */
 /* Load cnt <= P frames into slots [0,cnt): staged[j + cnt*i] channel values (ldpc_decoder_gpu.cu:218-273). */

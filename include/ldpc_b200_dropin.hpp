@@ -137,6 +137,28 @@ public:
   void decode(const dynamic_params_t &p_dyn_params, uint32_t p_num_vectors_to_process, void *p_input,
               const uint32_t *p_syndromes, uint32_t *p_results, report_t &report, uint32_t p_log = 0) {
     if (p_num_vectors_to_process == 0) return; // ldpc_decoder_gpu.cu:293-294
+    decode_on(&m_dec, 1, p_dyn_params, p_num_vectors_to_process, p_input, p_syndromes, p_results, report, p_log);
+  }
+
+  // EXTENSION (the reference drives device 0 only, h/cuda_manager.h:52): the same call on several
+  // decoders of this class, one per GPU (static parameter m_device), constructed from the same code and channel --
+  // one queue of frames, one host thread per device, a shared atomic cursor (ldpc_b200_decode_multi); the arrays and
+  // the report are those of decode().
+  static void decode_multi(decoder *const *p_decoders, uint32_t p_num_decoders, const dynamic_params_t &p_dyn_params,
+                           uint32_t p_num_vectors_to_process, void *p_input, const uint32_t *p_syndromes,
+                           uint32_t *p_results, report_t &report, uint32_t p_log = 0) {
+    if (!p_decoders || !p_num_decoders) throw error_t(std::string("decode_multi needs at least one decoder"));
+    if (p_num_vectors_to_process == 0) return;
+    std::vector<ldpc_b200_decoder *> handles(p_num_decoders);
+    for (uint32_t i = 0; i < p_num_decoders; ++i) handles[i] = p_decoders[i]->m_dec;
+    p_decoders[0]->decode_on(handles.data(), p_num_decoders, p_dyn_params, p_num_vectors_to_process, p_input, p_syndromes,
+                             p_results, report, p_log);
+  }
+
+private:
+  void decode_on(ldpc_b200_decoder *const *p_handles, uint32_t p_num_handles, const dynamic_params_t &p_dyn_params,
+                 uint32_t p_num_vectors_to_process, void *p_input, const uint32_t *p_syndromes, uint32_t *p_results,
+                 report_t &report, uint32_t p_log) {
     ldpc_b200_decode_params prm = ldpc_b200_decode_params();
     std::vector<uint8_t> converted; // host copy holding LLRs, only for channels without a device conversion
     const int ch = int(m_channel.channel());
@@ -181,8 +203,12 @@ public:
     if (p_log >= 2) prm.flags |= LDPC_B200_FLAG_TIME_KERNELS;
     std::vector<uint32_t> iters(p_log >= 3 ? p_num_vectors_to_process : 0);
     ldpc_b200_report rep;
-    check(ldpc_b200_decode(m_dec, &prm, p_num_vectors_to_process, p_input, p_syndromes, p_results, &rep,
-                           p_log >= 3 ? iters.data() : nullptr));
+    if (p_num_handles == 1)
+      check(ldpc_b200_decode(p_handles[0], &prm, p_num_vectors_to_process, p_input, p_syndromes, p_results, &rep,
+                             p_log >= 3 ? iters.data() : nullptr));
+    else
+      check(ldpc_b200_decode_multi(p_handles, p_num_handles, &prm, p_num_vectors_to_process, p_input, p_syndromes,
+                                   p_results, &rep, nullptr, p_log >= 3 ? iters.data() : nullptr, 0));
     report.max_iter = rep.max_iter;
     report.min_iter = rep.min_iter;
     report.avg_iter = rep.avg_iter;
@@ -210,6 +236,7 @@ public:
     }
   }
 
+public:
   bool decoding_input_is_llr() const { // h/ldpc_decoder_gpu.h:112-118
     const int ch = int(m_channel.channel());
     const bool has_kernel_for_llr_conversion = (ch == T::bsc_id) || (ch == T::awgn_id);

@@ -153,6 +153,30 @@ class Decoder:
                                            _ptr(results), C.byref(rep), _ptr(iters)))
         return results, iters, {k: getattr(rep, k) for k, _ in _lib.Report._fields_}
 
+    def decode_from_queue(self, queue: "FrameQueue", channel: int, channel_param: float, inputs, syndromes, results,
+                          iter_counts: np.ndarray | None = None, num_iter_max: int = 100, num_iter_check_parity: int = 10,
+                          layout=LAYOUT_INTERLEAVED, pool_frames: int = 0, flags: int = 0, frame_stride: int = 0,
+                          lookahead: int = 0):
+        """Decode the frames this decoder manages to reserve from a shared queue (one decoder per GPU; call it
+        concurrently from one thread or process per decoder).  inputs / syndromes / results / iter_counts are sized
+        for the whole queue (or a pool); returns (iter_counts, report) with report['frames_decoded']."""
+        n = queue.size
+        if isinstance(inputs, np.ndarray):
+            in_dtype = np.uint32 if layout == LAYOUT_PACKED_BITS else (np.float16 if flags & FLAG_HALF_INPUT else self.np_dtype)
+            inputs = np.ascontiguousarray(inputs, dtype=in_dtype)
+        if isinstance(syndromes, np.ndarray):
+            syndromes = np.ascontiguousarray(syndromes, dtype=np.uint32)
+        if iter_counts is None:
+            iter_counts = np.zeros(n, dtype=np.uint32)
+        prm = _lib.DecodeParams(channel=channel, channel_param=channel_param, num_iter_max=num_iter_max,
+                                num_iter_check_parity=num_iter_check_parity, input_layout=layout,
+                                frame_stride=frame_stride, input_pool_frames=pool_frames, flags=flags,
+                                queue_lookahead_frames=lookahead)
+        rep = _lib.Report()
+        _check(_lib.lib().ldpc_b200_decode_from_queue(self._h, C.byref(prm), queue._h, _ptr(inputs), _ptr(syndromes),
+                                                      _ptr(results), C.byref(rep), _ptr(iter_counts)))
+        return iter_counts, {k: getattr(rep, k) for k, _ in _lib.Report._fields_}
+
     def synthesize_frames(self, channel: int, noise: float, start_idx: int, n_frames: int, d_input, d_syndromes,
                           d_ref_bits):
         """Fill CUDA tensors with the reference harness' frames start_idx.. (generated on the device)."""
@@ -208,6 +232,60 @@ class Decoder:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.lib().ldpc_b200_decoder_destroy(self._h)
             self._h = None
+
+
+class FrameQueue:
+    """A queue of frames shared by several decoders (include/ldpc_b200.h, "one frame queue, several GPUs"): an atomic
+    cursor handing out blocks of consecutive frames.  shm_name: POSIX shared-memory name for one process per GPU (one
+    process creates, the others open with create=False); None: private to this process."""
+
+    def __init__(self, n_frames: int = 0, block_frames: int = 0, shm_name: str | None = None, create: bool = True):
+        h = C.c_void_p()
+        _check(_lib.lib().ldpc_b200_queue_create(shm_name.encode() if shm_name else None, int(create), n_frames,
+                                                 block_frames, C.byref(h)))
+        self._h = h
+        self.size = int(_lib.lib().ldpc_b200_queue_size(h))
+
+    def reset(self):
+        _lib.lib().ldpc_b200_queue_reset(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.lib().ldpc_b200_queue_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def decode_multi(decoders, channel: int, channel_param: float, inputs, syndromes, n_frames: int | None = None,
+                 num_iter_max: int = 100, num_iter_check_parity: int = 10, results=None, layout=LAYOUT_INTERLEAVED,
+                 pool_frames: int = 0, flags: int = 0, frame_stride: int = 0, block_frames: int = 0, lookahead: int = 0):
+    """One queue of frames decoded by several decoders (one per GPU) of ONE process: a host thread per decoder and a
+    shared atomic cursor inside the library (ldpc_b200_decode_multi).  Host buffers, or buffers every device can
+    address.  Returns (results, iter_counts, merged report, per-decoder reports)."""
+    d0 = decoders[0]
+    if isinstance(inputs, np.ndarray):
+        in_dtype = np.uint32 if layout == LAYOUT_PACKED_BITS else (np.float16 if flags & FLAG_HALF_INPUT else d0.np_dtype)
+        inputs = np.ascontiguousarray(inputs, dtype=in_dtype)
+        if n_frames is None:
+            n_frames = inputs.shape[1] if layout == LAYOUT_INTERLEAVED else inputs.shape[0]
+    if isinstance(syndromes, np.ndarray):
+        syndromes = np.ascontiguousarray(syndromes, dtype=np.uint32)
+    assert n_frames is not None
+    if results is None:
+        results = np.zeros((n_frames, d0.code.n_vars // 32), dtype=np.uint32)
+    iters = np.zeros(n_frames, dtype=np.uint32)
+    prm = _lib.DecodeParams(channel=channel, channel_param=channel_param, num_iter_max=num_iter_max,
+                            num_iter_check_parity=num_iter_check_parity, input_layout=layout, frame_stride=frame_stride,
+                            input_pool_frames=pool_frames, flags=flags, queue_lookahead_frames=lookahead)
+    handles = (C.c_void_p * len(decoders))(*[d._h for d in decoders])
+    rep = _lib.Report()
+    per = (_lib.Report * len(decoders))()
+    _check(_lib.lib().ldpc_b200_decode_multi(handles, len(decoders), C.byref(prm), n_frames, _ptr(inputs), _ptr(syndromes),
+                                             _ptr(results), C.byref(rep), per, _ptr(iters), block_frames))
+    as_dict = lambda r: {k: getattr(r, k) for k, _ in _lib.Report._fields_}  # noqa: E731
+    return results, iters, as_dict(rep), [as_dict(r) for r in per]
 
 
 def phi_abs_f32(x: np.ndarray) -> np.ndarray:

@@ -35,7 +35,8 @@ class Config(C.Structure):
 class DecodeParams(C.Structure):
     _fields_ = [("channel", C.c_int32), ("channel_param", C.c_float), ("num_iter_max", C.c_uint32),
                 ("num_iter_check_parity", C.c_uint32), ("input_layout", C.c_int32), ("frame_stride", C.c_uint64),
-                ("input_pool_frames", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("input_pool_frames", C.c_uint32), ("flags", C.c_uint32), ("queue_lookahead_frames", C.c_uint32),
+                ("reserved", C.c_uint32 * 3)]
 
 
 class Report(C.Structure):
@@ -46,7 +47,8 @@ class Report(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("check_s", C.c_double), ("retire_s", C.c_double), ("refill_s", C.c_double),
                 ("frames_refilled", C.c_uint64), ("graph_launches", C.c_uint64),
-                ("slot_iterations", C.c_uint64), ("cn_refill_launches", C.c_uint64), ("cn_refill_s", C.c_double)]
+                ("slot_iterations", C.c_uint64), ("cn_refill_launches", C.c_uint64), ("cn_refill_s", C.c_double),
+                ("frames_decoded", C.c_uint64)]
 
 
 # every symbol include/ldpc_b200.h declares: name -> (restype, argtypes)
@@ -65,6 +67,14 @@ SYMBOLS = {
     "ldpc_b200_decoder_prepare_host_io": (C.c_int, [C.c_void_p]),
     "ldpc_b200_decode": (C.c_int, [C.c_void_p, C.POINTER(DecodeParams), C.c_uint32, _VP, _VP, _VP,
                                    C.POINTER(Report), _VP]),
+    "ldpc_b200_queue_create": (C.c_int, [C.c_char_p, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "ldpc_b200_queue_destroy": (None, [C.c_void_p]),
+    "ldpc_b200_queue_size": (C.c_uint32, [C.c_void_p]),
+    "ldpc_b200_queue_reset": (None, [C.c_void_p]),
+    "ldpc_b200_decode_from_queue": (C.c_int, [C.c_void_p, C.POINTER(DecodeParams), C.c_void_p, _VP, _VP, _VP,
+                                              C.POINTER(Report), _VP]),
+    "ldpc_b200_decode_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(DecodeParams), C.c_uint32, _VP, _VP,
+                                         _VP, C.POINTER(Report), C.POINTER(Report), _VP, C.c_uint32]),
     "ldpc_b200_debug_refill": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_uint32, _VP, _VP]),
     "ldpc_b200_debug_iterate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(C.c_float),
                                           C.POINTER(C.c_float)]),

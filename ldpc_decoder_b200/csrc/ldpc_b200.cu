@@ -12,6 +12,7 @@
 #include "ldpc_synth.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,10 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -938,6 +943,89 @@ dev::SchedConst make_sched_const(const ldpc_b200_decoder *d, const ldpc_b200_dec
 
 } // namespace
 
+// ------------------------------------------------------------------ shared frame queue
+// "a single host-side atomic cursor over the frame queue gives dynamic load balance" (the reference
+// hard-codes device 0, h/cuda_manager.h:52).  A queue is an atomic cursor over the rows of the caller's arrays; every
+// decoder drawing from it (one per GPU: threads of one process, or one process per GPU through POSIX shared memory)
+// reserves whole blocks of consecutive frames and decodes them as ONE continuous call -- frames keep being loaded into
+// freed slots across block boundaries, and only the end of the queue has a tail.
+struct queue_shared { // lives in the process heap or in a shared-memory mapping
+  std::atomic<uint64_t> cursor;
+  uint32_t n_total, block, magic, pad;
+};
+constexpr uint32_t kQueueMagic = 0x4C445043u;
+
+struct ldpc_b200_queue {
+  queue_shared *sh = nullptr;
+  queue_shared local;
+  size_t map_len = 0;
+  std::string shm_name;
+  bool owner = false;
+  ~ldpc_b200_queue() {
+    if (map_len) {
+      munmap(sh, map_len);
+      if (owner) shm_unlink(shm_name.c_str());
+    }
+  }
+};
+
+namespace {
+
+// one decoder's view of a queue: the blocks it has reserved so far, mirrored into mapped host memory for the
+// scheduler kernel (dev::FrameQueueView)
+struct local_queue {
+  ldpc_b200_queue *q = nullptr;
+  uint32_t block = 0, n_total = 0;
+  uint32_t avail = 0; // local frames reserved so far
+  bool final = false; // the cursor has passed the end: nothing more will come
+  std::vector<uint32_t> starts;
+  uint32_t *h_blk = nullptr;          // mapped pinned [max_blocks], 0xFFFFFFFF = not written
+  volatile uint32_t *h_ctl = nullptr; // mapped pinned [2]: avail, final
+  uint32_t max_blocks = 0;
+
+  ldpc_b200_status init(ldpc_b200_queue *queue) {
+    q = queue;
+    block = queue->sh->block;
+    n_total = queue->sh->n_total;
+    max_blocks = (n_total + block - 1) / block + 1;
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_blk), sizeof(uint32_t) * (size_t(max_blocks) + 2),
+                         cudaHostAllocPortable | cudaHostAllocMapped));
+    std::fill(h_blk, h_blk + max_blocks + 2, 0xFFFFFFFFu);
+    h_ctl = h_blk + max_blocks; // the two control words share the allocation
+    h_ctl[0] = 0;
+    h_ctl[1] = 0;
+    return LDPC_B200_OK;
+  }
+  ~local_queue() {
+    if (h_blk) cudaFreeHost(h_blk);
+  }
+  // reserve blocks until `want` local frames are available (or the queue is exhausted)
+  void reserve_upto(uint64_t want) {
+    while (!final && avail < want) {
+      const uint64_t start = q->sh->cursor.fetch_add(block, std::memory_order_relaxed);
+      if (start >= n_total) {
+        final = true;
+        break;
+      }
+      const uint32_t cnt = uint32_t(std::min<uint64_t>(block, n_total - start));
+      h_blk[starts.size()] = uint32_t(start);
+      starts.push_back(uint32_t(start));
+      std::atomic_thread_fence(std::memory_order_release); // the block start is visible before the count that covers it
+      avail += cnt;
+      h_ctl[0] = avail;
+      if (cnt < block) final = true; // a partial block is the last one of the queue
+    }
+    if (final) {
+      std::atomic_thread_fence(std::memory_order_release);
+      h_ctl[1] = 1;
+    }
+  }
+  uint32_t global_of(uint32_t f) const { return starts[f / block] + f % block; }
+  dev::FrameQueueView view() const { return dev::FrameQueueView{h_ctl, h_blk}; }
+};
+
+} // namespace
+
 // ------------------------------------------------------------------ host feed
 // Staging of host-resident frames into the device ring over the copy stream (the reference's prepare_vectors +
 // transfer_vectors, ldpc_decoder_gpu.cu:199-273, but gathered by all host threads, off the critical path and in
@@ -956,10 +1044,15 @@ struct host_feeder {
   uint64_t frame_stride = 0; // frame-major inputs: elements between frames
   uint32_t staged = 0;       // frames [0, staged) have been handed to the copy stream
   bool refill_recorded = false;
+  const local_queue *lq = nullptr; // frames are drawn from a shared queue: local index -> row of the caller's arrays
+
+  uint32_t col_of(uint32_t f) const { return (lq ? lq->global_of(f) : f) % n_cols; }
+  // consecutive local frames are consecutive rows of the caller's arrays only inside a queue block
+  uint32_t contiguous_from(uint32_t f) const { return lq ? lq->block - f % lq->block : 0xFFFFFFFFu; }
 
   ldpc_b200_status stage_upto(uint32_t upto) {
     if (!in_host && !syn_host) return LDPC_B200_OK;
-    upto = std::min(n_frames, upto);
+    upto = std::min(lq ? lq->avail : n_frames, upto);
     if (upto <= staged) return LDPC_B200_OK;
     CU_TRY(cudaStreamSynchronize(d->copy_stream)); // earlier copies out of the pinned mirror are done
     // ring positions being overwritten belong to frames already loaded; their refill kernels must have read them
@@ -988,8 +1081,8 @@ private:
     };
     std::vector<chunk_t> chunks; // the same for every variable row: computed once
     for (uint32_t f = f0; f < f1;) {
-      const uint32_t r = f % ring_frames, in_blk = r % ring_block, col = f % n_cols;
-      const uint32_t run = std::min({f1 - f, ring_block - in_blk, n_cols - col});
+      const uint32_t r = f % ring_frames, in_blk = r % ring_block, col = col_of(f);
+      const uint32_t run = std::min({f1 - f, ring_block - in_blk, n_cols - col, contiguous_from(f)});
       chunks.push_back({(size_t(r / ring_block) * n_reg * ring_block + in_blk) * es, size_t(col) * es, size_t(run) * es});
       f += run;
     }
@@ -1033,7 +1126,7 @@ private:
     parallel_for(f1 - f0, d->host_threads, [&](size_t a, size_t b) {
       for (size_t t = a; t < b; ++t) {
         const uint32_t f = f0 + uint32_t(t);
-        memcpy(mirror + size_t(f % ring_frames) * row_elems * es_fm, in_host + size_t(f % n_cols) * frame_stride * es_fm,
+        memcpy(mirror + size_t(f % ring_frames) * row_elems * es_fm, in_host + size_t(col_of(f)) * frame_stride * es_fm,
                size_t(row_elems) * es_fm);
       }
     });
@@ -1050,7 +1143,7 @@ private:
   ldpc_b200_status stage_syndromes(uint32_t f0, uint32_t f1) {
     const uint32_t S = d->S;
     for (uint32_t f = f0; f < f1; ++f)
-      memcpy(d->h_stage_syn.p + size_t(f % ring_frames) * S, syn_host + size_t(f % n_cols) * S, size_t(S) * 4);
+      memcpy(d->h_stage_syn.p + size_t(f % ring_frames) * S, syn_host + size_t(col_of(f)) * S, size_t(S) * 4);
     for (uint32_t f = f0; f < f1;) {
       const uint32_t r = f % ring_frames, run = std::min(f1 - f, ring_frames - r);
       CU_TRY(cudaMemcpyAsync(d->d_stage_syn.p + size_t(r) * S, d->h_stage_syn.p + size_t(r) * S, size_t(run) * S * 4,
@@ -1064,17 +1157,11 @@ private:
 
 } // namespace
 
-extern "C" {
-
-// decode(): the reference's scheduling semantics (ldpc_decoder_gpu.cu:283-634) with the decisions taken on
-// the device.  Per check period the compute stream runs
-//     [CN, VN] x k  ->  syndrome check  ->  sched_kernel  ->  extract  ->  refill
-// without waiting for the host; the host only (a) keeps one period of work queued ahead, (b) stages the next
-// frames into a device ring over pinned cudaMemcpyAsync on the copy stream while the flood iterations run,
-// (c) drains retired frames' packed decisions on the copy stream, (d) watches the summary for the end.
-ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm, uint32_t n_frames,
-                                  const void *input, const uint32_t *syndromes, uint32_t *results,
-                                  ldpc_b200_report *report, uint32_t *iter_counts) {
+// queue == nullptr: the classic call, frames 0..n_frames-1.  Otherwise n_frames is the size of the queue (= rows of the
+// caller's arrays) and this decoder decodes whatever blocks of it it manages to reserve.
+static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm, uint32_t n_frames,
+                                    const void *input, const uint32_t *syndromes, uint32_t *results,
+                                    ldpc_b200_report *report, uint32_t *iter_counts, ldpc_b200_queue *queue) {
   if (!d || !prm) return fail(LDPC_B200_ERR_INVALID, "null argument");
   if (n_frames == 0) return LDPC_B200_OK; // ldpc_decoder_gpu.cu:293-294
   if (!input || !syndromes || !results) return fail(LDPC_B200_ERR_INVALID, "null buffer");
@@ -1083,12 +1170,27 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   const double t0 = now_s();
   ldpc_b200_report rep;
   memset(&rep, 0, sizeof(rep));
+  if (report) *report = rep;
+
+  // ---- shared queue: reserve the first batch now; later reservations keep `ahead` frames beyond what is loaded
+  local_queue lq_store, *lq = nullptr;
+  if (queue) {
+    if (prm->flags & LDPC_B200_FLAG_SIMD_PAIRS)
+      return fail(LDPC_B200_ERR_INVALID, "SIMD_PAIRS is not available when decoding from a shared queue");
+    if (queue->sh->n_total != n_frames) return fail(LDPC_B200_ERR_INVALID, "queue size differs from n_frames");
+    const ldpc_b200_status qs = lq_store.init(queue);
+    if (qs != LDPC_B200_OK) return qs;
+    lq = &lq_store;
+    lq->reserve_upto(d->frames_in_flight);
+    if (lq->avail == 0) return LDPC_B200_OK; // the other decoders have taken the whole queue
+  }
+  const uint32_t queue_ahead = prm->queue_lookahead_frames ? prm->queue_lookahead_frames : d->frames_in_flight;
 
   const bool in_dev = is_device_pointer(input), syn_dev = is_device_pointer(syndromes);
   const bool res_dev = is_device_pointer(results);
   const bool simd_pairs = (prm->flags & LDPC_B200_FLAG_SIMD_PAIRS) != 0;
   const bool time_kernels = (prm->flags & LDPC_B200_FLAG_TIME_KERNELS) != 0;
-  const uint32_t B = std::min(n_frames, d->frames_in_flight); // num_vectors_gpu_batch
+  const uint32_t B = std::min(lq ? lq->avail : n_frames, d->frames_in_flight); // num_vectors_gpu_batch
   const uint32_t k_check = prm->num_iter_check_parity;
   // even-count refills can never load an odd remainder (the reference's OpenCL harness only ever feeds
   // parallel_factor * loading_factor frames, ldpc_decoder_gpu.cpp:623 / main.cpp:320)
@@ -1110,6 +1212,9 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     return fail(LDPC_B200_ERR_INVALID, "HALF_INPUT is the transfer format of an FP32 decoder (an FP16 decoder takes halves anyway)");
   const int src_kind = packed ? dev::kSrcPackedBits : (half_input ? dev::kSrcHalf : dev::kSrcNative);
   dev::SchedConst sc = make_sched_const(d, prm, n_frames, in_dev, syn_dev, res_dev);
+  sc.batch = B;
+  sc.queue_block = lq ? lq->block : 0u;
+  const dev::FrameQueueView qview = lq ? lq->view() : dev::FrameQueueView{nullptr, nullptr};
   // fused refill, decided per period by the scheduler kernel (see select_kernels): threshold in frames
   sc.fused_min_new = 0xFFFFFFFFu;
   if (d->k_cn_refill) sc.fused_min_new = d->fused_mode == 1 ? 1u : std::max<uint32_t>(1u, uint32_t(uint64_t(d->P) * d->fused_min_pct / 100));
@@ -1151,6 +1256,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   feed.es = half_input ? 2 : d->elem;
   feed.es_fm = packed ? 4 : (half_input ? 2 : d->elem);
   feed.frame_stride = sc.frame_stride;
+  feed.lq = lq;
   auto stage_upto = [&](uint32_t upto) { return feed.stage_upto(upto); };
 
   // ---- optional per-launch timing (LDPC_B200_FLAG_TIME_KERNELS): see launch_timer
@@ -1180,7 +1286,8 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   CU_TRY(cudaEventRecord(ev_first, d->stream));
   dev::sched_init_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(sc, d->d_state.p, d->d_in_gpu.p, d->d_virt.p,
                                                                   d_iter_start, d_iter_end, d->d_refill.p, d->d_n_new.p,
-                                                                  d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p);
+                                                                  d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p,
+                                                                  qview);
   auto enqueue_refill = [&]() {
     if (fused_any) {
       d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, false, dev::kGateFused, true);
@@ -1237,7 +1344,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
     dev::sched_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(
         sc, d->d_state.p, d->d_viol.p, d->d_in_gpu.p, d->d_virt.p, d_iter_start, d_iter_end, d->d_refill.p,
         d->d_extract.p, d->d_n_new.p, d->d_new_mask.p, d->d_retire_mask.p, d->d_slot_entry.p, d->d_retired.p,
-        d->d_summary.p, d->d_scratch.p, d->d_moves.p, d->d_n_moves.p);
+        d->d_summary.p, d->d_scratch.p, d->d_moves.p, d->d_n_moves.p, qview);
     d->launch_extract_kernel(res_dst_dev);
     if (sc.early_retire) { // tail compaction of the frames still running (no-op unless the scheduler asked for moves)
       if (d->elem == 4)
@@ -1296,7 +1403,8 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
         const uint32_t *frames = d->h_retired.p + size_t(hp) * d->P;
         parallel_for(sm.n_retired, d->host_threads, [&](size_t a, size_t b2) {
           for (size_t t = a; t < b2; ++t)
-            memcpy(results + size_t(frames[t]) * d->W, d->h_results.p + t * d->W, size_t(d->W) * 4);
+            memcpy(results + size_t(lq ? lq->global_of(frames[t]) : frames[t]) * d->W, d->h_results.p + t * d->W,
+                   size_t(d->W) * 4);
         });
         rep.d2h_bytes += bytes + sizeof(uint32_t) * B;
       }
@@ -1307,6 +1415,7 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
       rep.slot_iterations += uint64_t(k_check) << sm.log2_p_active; // the k iterations that follow this check
     }
     // frames the next refill may need: at most B beyond what has been loaded so far
+    if (lq) lq->reserve_upto(uint64_t(next_known) + queue_ahead);
     st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, uint64_t(next_known) + B)));
     if (st != LDPC_B200_OK) return st;
     // service of this period + the next period's flood iterations (run ahead: no-ops once the scheduler has
@@ -1366,23 +1475,161 @@ ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_p
   rep.other_launches -= 1 + (fused_any ? 1 : 0);
   rep.n_checks_run -= 1;
 
-  // per-frame iteration counters live on the device (:616-628)
+  // per-frame iteration counters live on the device (:616-628), indexed by this decoder's local frame numbers
+  const uint32_t n_local = lq ? next_known : n_frames; // frames this decoder loaded (all of them, for a classic call)
   std::vector<uint32_t> it(2ull * n_frames);
   CU_TRY(cudaMemcpy(it.data(), d->d_iter.p, sizeof(uint32_t) * 2ull * n_frames, cudaMemcpyDeviceToHost));
   rep.max_iter = 0;
   rep.min_iter = uint32_t(-1);
   double avg = 0;
-  for (uint32_t j = 0; j < n_frames; ++j) {
+  for (uint32_t j = 0; j < n_local; ++j) {
     const uint32_t n = it[n_frames + j] - it[j];
     rep.max_iter = std::max(rep.max_iter, n);
     rep.min_iter = std::min(rep.min_iter, n);
     avg += n;
-    if (iter_counts) iter_counts[j] = n;
+    if (iter_counts) iter_counts[lq ? lq->global_of(j) : j] = n;
   }
-  rep.avg_iter = float(avg / n_frames);
+  rep.frames_decoded = n_local;
+  rep.avg_iter = float(avg / n_local);
   rep.iter_time_per_vector = rep.global_iters ? float(rep.device_s / (double(rep.global_iters) * B)) : 0.f;
   rep.elapsed_s = now_s() - t0;
   if (report) *report = rep;
+  return LDPC_B200_OK;
+}
+
+extern "C" {
+
+// decode(): the reference's scheduling semantics (ldpc_decoder_gpu.cu:283-634) with the decisions taken on
+// the device.  Per check period the compute stream runs
+//     [CN, VN] x k  ->  syndrome check  ->  sched_kernel  ->  extract  ->  refill
+// without waiting for the host; the host only (a) keeps one period of work queued ahead, (b) stages the next
+// frames into a device ring over pinned cudaMemcpyAsync on the copy stream while the flood iterations run,
+// (c) drains retired frames' packed decisions on the copy stream, (d) watches the summary for the end.
+ldpc_b200_status ldpc_b200_decode(ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm, uint32_t n_frames,
+                                  const void *input, const uint32_t *syndromes, uint32_t *results,
+                                  ldpc_b200_report *report, uint32_t *iter_counts) {
+  return decode_impl(d, prm, n_frames, input, syndromes, results, report, iter_counts, nullptr);
+}
+
+// ------------------------------------------------------------------ shared frame queue: C ABI
+ldpc_b200_status ldpc_b200_queue_create(const char *shm_name, int32_t create, uint32_t n_frames, uint32_t block_frames,
+                                        ldpc_b200_queue **out) {
+  if (!out) return fail(LDPC_B200_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  std::unique_ptr<ldpc_b200_queue> q(new ldpc_b200_queue);
+  if (!shm_name) { // private to this process
+    if (!n_frames || !block_frames) return fail(LDPC_B200_ERR_INVALID, "queue needs a size and a block size");
+    q->sh = &q->local;
+    q->sh->cursor.store(0);
+    q->sh->n_total = n_frames;
+    q->sh->block = block_frames;
+    q->sh->magic = kQueueMagic;
+  } else {
+    q->shm_name = shm_name[0] == '/' ? shm_name : std::string("/") + shm_name;
+    if (create && (!n_frames || !block_frames)) return fail(LDPC_B200_ERR_INVALID, "queue needs a size and a block size");
+    if (create) shm_unlink(q->shm_name.c_str()); // a stale object of a crashed run
+    const int fd = shm_open(q->shm_name.c_str(), create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return fail(LDPC_B200_ERR_IO, "shm_open(" + q->shm_name + ") failed");
+    if (create && ftruncate(fd, sizeof(queue_shared)) != 0) {
+      close(fd);
+      return fail(LDPC_B200_ERR_IO, "ftruncate on the shared queue failed");
+    }
+    void *m = mmap(nullptr, sizeof(queue_shared), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return fail(LDPC_B200_ERR_IO, "mmap of the shared queue failed");
+    q->sh = static_cast<queue_shared *>(m);
+    q->map_len = sizeof(queue_shared);
+    q->owner = create != 0;
+    if (create) {
+      new (&q->sh->cursor) std::atomic<uint64_t>(0);
+      q->sh->n_total = n_frames;
+      q->sh->block = block_frames;
+      std::atomic_thread_fence(std::memory_order_release);
+      q->sh->magic = kQueueMagic;
+    } else if (q->sh->magic != kQueueMagic) {
+      return fail(LDPC_B200_ERR_INVALID, "shared queue is not initialised (open it after the creating process returned)");
+    }
+  }
+  *out = q.release();
+  return LDPC_B200_OK;
+}
+
+void ldpc_b200_queue_destroy(ldpc_b200_queue *q) { delete q; }
+
+uint32_t ldpc_b200_queue_size(const ldpc_b200_queue *q) { return q ? q->sh->n_total : 0; }
+
+void ldpc_b200_queue_reset(ldpc_b200_queue *q) {
+  if (q) q->sh->cursor.store(0);
+}
+
+ldpc_b200_status ldpc_b200_decode_from_queue(ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm,
+                                             ldpc_b200_queue *queue, const void *input, const uint32_t *syndromes,
+                                             uint32_t *results, ldpc_b200_report *report, uint32_t *iter_counts) {
+  if (!queue) return fail(LDPC_B200_ERR_INVALID, "null queue");
+  return decode_impl(d, prm, queue->sh->n_total, input, syndromes, results, report, iter_counts, queue);
+}
+
+// One queue, one host thread per decoder (= per GPU).  The merged report sums the counters, takes the longest
+// elapsed / device time and the iteration statistics over all frames.
+ldpc_b200_status ldpc_b200_decode_multi(ldpc_b200_decoder *const *decs, uint32_t n_decs,
+                                        const ldpc_b200_decode_params *prm, uint32_t n_frames, const void *input,
+                                        const uint32_t *syndromes, uint32_t *results, ldpc_b200_report *report,
+                                        ldpc_b200_report *per_decoder, uint32_t *iter_counts, uint32_t block_frames) {
+  if (!decs || !n_decs || !prm) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  if (n_frames == 0) return LDPC_B200_OK;
+  uint32_t blk = block_frames;
+  if (!blk) { // default: fine enough to balance, coarse enough that a block is a few host-staging runs
+    blk = 256;
+    for (uint32_t i = 0; i < n_decs; ++i)
+      if (decs[i]) blk = std::min(blk, std::max(32u, decs[i]->frames_in_flight));
+  }
+  ldpc_b200_queue *q = nullptr;
+  ldpc_b200_status st = ldpc_b200_queue_create(nullptr, 1, n_frames, blk, &q);
+  if (st != LDPC_B200_OK) return st;
+  std::unique_ptr<ldpc_b200_queue> guard(q);
+  std::vector<ldpc_b200_report> reps(n_decs);
+  std::vector<ldpc_b200_status> sts(n_decs, LDPC_B200_OK);
+  std::vector<std::string> errs(n_decs);
+  std::vector<std::thread> threads;
+  for (uint32_t i = 0; i < n_decs; ++i)
+    threads.emplace_back([&, i] {
+      memset(&reps[i], 0, sizeof(ldpc_b200_report));
+      sts[i] = ldpc_b200_decode_from_queue(decs[i], prm, q, input, syndromes, results, &reps[i], iter_counts);
+      if (sts[i] != LDPC_B200_OK) errs[i] = g_last_error; // thread-local: carry it to the caller's thread
+    });
+  for (std::thread &t : threads) t.join();
+  for (uint32_t i = 0; i < n_decs; ++i)
+    if (sts[i] != LDPC_B200_OK) return fail(sts[i], "decoder " + std::to_string(i) + ": " + errs[i]);
+  ldpc_b200_report m;
+  memset(&m, 0, sizeof(m));
+  m.min_iter = uint32_t(-1);
+  double avg = 0;
+  for (uint32_t i = 0; i < n_decs; ++i) {
+    const ldpc_b200_report &r = reps[i];
+    if (per_decoder) per_decoder[i] = r;
+    if (!r.frames_decoded) continue;
+    m.max_iter = std::max(m.max_iter, r.max_iter);
+    m.min_iter = std::min(m.min_iter, r.min_iter);
+    avg += double(r.avg_iter) * double(r.frames_decoded);
+    m.frames_decoded += r.frames_decoded;
+    m.global_iters = std::max(m.global_iters, r.global_iters);
+    m.n_checks_run += r.n_checks_run;
+    m.elapsed_s = std::max(m.elapsed_s, r.elapsed_s);
+    m.device_s = std::max(m.device_s, r.device_s);
+    m.cn_s += r.cn_s, m.vn_s += r.vn_s, m.check_s += r.check_s, m.retire_s += r.retire_s, m.refill_s += r.refill_s;
+    m.cn_refill_s += r.cn_refill_s;
+    m.cn_launches += r.cn_launches, m.vn_launches += r.vn_launches, m.other_launches += r.other_launches;
+    m.cn_refill_launches += r.cn_refill_launches;
+    m.h2d_bytes += r.h2d_bytes, m.d2h_bytes += r.d2h_bytes;
+    m.frames_refilled += r.frames_refilled, m.graph_launches += r.graph_launches, m.slot_iterations += r.slot_iterations;
+  }
+  m.avg_iter = m.frames_decoded ? float(avg / double(m.frames_decoded)) : 0.f;
+  // the reference's per-frame iteration time (ldpc_decoder_gpu.cu:627) over the frames in flight on all devices
+  double slots = 0;
+  for (uint32_t i = 0; i < n_decs; ++i)
+    if (reps[i].iter_time_per_vector > 0) slots += 1.0 / reps[i].iter_time_per_vector;
+  m.iter_time_per_vector = slots > 0 ? float(1.0 / slots) : 0.f;
+  if (report) *report = m;
   return LDPC_B200_OK;
 }
 

@@ -495,12 +495,11 @@ __global__ void __launch_bounds__(cn_threads_for(kMaxRegDeg), min_blocks_for(kMa
                                              gate);
 }
 
-// first check-node pass after a refill (one launch per check period): message and prior vectors of a row are both in
-// registers, so it runs 2 CTAs/SM with twice the loads in flight per thread
-// (ptxas fits the kernel into 80 and even 64 registers without spills -- LDPC_CN_REFILL_MINBLOCKS=3 / 4 -- by
-// serialising the prior gathers; not yet measured against this setting: first A/B of the next round.)
+// first check-node pass after a refill (one launch per check period that loads frames): message and prior vectors of a
+// row are both live.  A/B on B200 in whole bench steps (profiles/r06_ab_fused_refill.txt): 2 CTAs/SM (122 registers) 16.4
+// ms per fused pass, 3 CTAs/SM (80 registers, prior gathers partly serialised) 15.2 ms, 4 CTAs/SM (64 registers) 17.3 ms.
 #ifndef LDPC_CN_REFILL_MINBLOCKS
-#define LDPC_CN_REFILL_MINBLOCKS 2
+#define LDPC_CN_REFILL_MINBLOCKS 3
 #endif
 template <class Tr, int kMaxRegDeg, class Idx>
 __global__ void __launch_bounds__(kThreads, LDPC_CN_REFILL_MINBLOCKS)
@@ -1093,6 +1092,17 @@ struct SchedConst {
   uint32_t early_retire, log2_v /* log2 frames per 16-byte vector */, min_log2_p_active;
   // a period that loads at least this many frames fuses its refill into its first check-node pass (0xFFFFFFFF: never)
   uint32_t fused_min_new;
+  // Shared frame queue (ldpc_b200_decode_from_queue: several decoders, one per GPU, draw from one queue): this decoder
+  // numbers the frames it has been handed 0, 1, 2, ... ("local" index: iteration counters, staging ring); they are
+  // whole blocks of queue_block consecutive frames of the caller's arrays, block i starting at global frame
+  // FrameQueueView::block_start[i].  queue_block = 0: classic call, local index = global frame index.
+  uint32_t queue_block, pad3;
+};
+// what the scheduler kernel reads of the queue: HOST memory mapped into the device (cudaHostAllocMapped), so that a
+// scheduler kernel enqueued one period ahead still sees what the host thread has reserved since
+struct FrameQueueView {
+  const volatile uint32_t *ctl;     // [0] = local frames reserved so far, [1] = 1 once no more frames will come
+  const volatile uint32_t *block_start; // [i] = first global frame of local block i (0xFFFFFFFF: not written yet)
 };
 struct SchedState {
   uint32_t next_to_load, g;
@@ -1111,8 +1121,29 @@ struct SlotMove {
   uint32_t src, dst;
 };
 
-__device__ __forceinline__ void make_refill_entry(const SchedConst &c, uint32_t frame, uint32_t slot, RefillEntry &en) {
-  const uint32_t col = frame % c.n_cols;
+// global frame index (row of the caller's arrays) of local frame f
+__device__ __forceinline__ uint32_t global_frame(const SchedConst &c, const FrameQueueView &q, uint32_t f) {
+  if (c.queue_block == 0) return f;
+  return q.block_start[f / c.queue_block] + f % c.queue_block;
+}
+// frames of the queue this decoder may load now, and whether that is all it will ever get
+__device__ __forceinline__ void queue_state(const SchedConst &c, const FrameQueueView &q, uint32_t &avail, uint32_t &final) {
+  avail = c.n_frames;
+  final = 1;
+  if (c.queue_block) {
+    avail = q.ctl[0];
+    final = q.ctl[1];
+    // a block whose start has not become visible yet is not available (the host writes the start first)
+    while (avail && q.block_start[(avail - 1) / c.queue_block] == 0xFFFFFFFFu) {
+      avail = ((avail - 1) / c.queue_block) * c.queue_block;
+      final = 0;
+    }
+  }
+}
+
+__device__ __forceinline__ void make_refill_entry(const SchedConst &c, const FrameQueueView &q, uint32_t frame, uint32_t slot,
+                                                  RefillEntry &en) {
+  const uint32_t col = global_frame(c, q, frame) % c.n_cols;
   if (c.input_mode == 0) {
     en.src_offset = col;
     en.src_stride = c.n_cols;
@@ -1166,7 +1197,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
 __global__ void __launch_bounds__(kSchedThreads)
     sched_init_kernel(SchedConst c, SchedState *st, uint32_t *in_gpu, uint32_t *virt, uint32_t *iter_start,
                       uint32_t *iter_end, RefillEntry *entries, uint32_t *n_new_out, uint32_t *new_mask,
-                      uint32_t *retire_mask, uint32_t *slot_entry) {
+                      uint32_t *retire_mask, uint32_t *slot_entry, FrameQueueView q) {
   const uint32_t PW = (1u << c.log2_p) >> 5;
   for (uint32_t i = threadIdx.x; i < c.n_frames; i += blockDim.x) iter_start[i] = iter_end[i] = 0xFFFFFFFFu;
   for (uint32_t w = threadIdx.x; w < PW; w += blockDim.x) {
@@ -1177,7 +1208,7 @@ __global__ void __launch_bounds__(kSchedThreads)
   for (uint32_t j = threadIdx.x; j < c.batch; j += blockDim.x) {
     in_gpu[j] = virt[j] = j;
     slot_entry[j] = j;
-    make_refill_entry(c, j, j, entries[j]);
+    make_refill_entry(c, q, j, j, entries[j]);
   }
   if (threadIdx.x == 0) {
     st->next_to_load = c.batch;
@@ -1197,13 +1228,24 @@ __global__ void __launch_bounds__(kSchedThreads)
                  uint32_t *iter_start, uint32_t *iter_end, RefillEntry *entries, ExtractEntry *slot_dst,
                  uint32_t *n_new_out, uint32_t *new_mask, uint32_t *retire_mask, uint32_t *slot_entry,
                  uint32_t *retired_frames, SchedSummary *summary, uint32_t *scratch /* [2P] */, SlotMove *moves,
-                 uint32_t *n_moves_out) {
+                 uint32_t *n_moves_out, FrameQueueView q) {
   __shared__ uint8_t s_stop[kMaxSlots];
   __shared__ uint32_t s_partner[kMaxSlots]; // finished positions >= n_new, compacted in position order
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_n_new, s_all_done;
+  __shared__ uint32_t s_n_new, s_all_done, s_avail, s_final;
   const uint32_t B = st->batch_active, PW = (1u << c.log2_p) >> 5, tid = threadIdx.x;
-  if (tid == 0) *n_moves_out = 0;
+  if (tid == 0) {
+    *n_moves_out = 0;
+    uint32_t avail, final;
+    queue_state(c, q, avail, final);
+    s_avail = avail;
+    s_final = final;
+  }
+  __syncthreads();
+  // frames this decoder can load at this check (all of the call's frames unless it draws from a shared queue), and
+  // whether the input is exhausted once they are loaded
+  const uint32_t avail = s_avail;
+  const bool input_final = s_final != 0;
   if (st->done) { // run-ahead period after the end: nothing to retire or load
     for (uint32_t w = tid; w < PW; w += blockDim.x) new_mask[w] = retire_mask[w] = 0;
     if (tid == 0) {
@@ -1231,7 +1273,7 @@ __global__ void __launch_bounds__(kSchedThreads)
       if (iter_end[f] == 0xFFFFFFFFu) iter_end[f] = g;
     }
   }
-  if (c.early_retire && next == c.n_frames) {
+  if (c.early_retire && input_final && next == avail) {
     // ---- input exhausted, early-retire mode: every stopped frame leaves now; survivors are compacted
     __shared__ uint32_t s_occ[kMaxSlots / 32];
     __shared__ uint32_t s_p_new;
@@ -1247,7 +1289,7 @@ __global__ void __launch_bounds__(kSchedThreads)
       if (s_stop[j]) {
         const uint32_t t = rank_stop++;
         atomicOr(retire_mask + (s >> 5), 1u << (s & 31u));
-        slot_dst[s].dst_offset = c.results_ring ? uint64_t(t) * c.res_words : uint64_t(f) * c.res_words;
+        slot_dst[s].dst_offset = c.results_ring ? uint64_t(t) * c.res_words : uint64_t(global_frame(c, q, f)) * c.res_words;
         retired_frames[t] = f;
       } else {
         const uint32_t k = rank_keep++;
@@ -1325,8 +1367,8 @@ __global__ void __launch_bounds__(kSchedThreads)
   uint32_t n_stop;
   block_exclusive_scan(my_stop, s_warp, n_stop);
   if (tid == 0) {
-    const uint32_t remaining = c.n_frames - next;
-    s_all_done = (remaining == 0 && n_stop == B); // :414
+    const uint32_t remaining = avail > next ? avail - next : 0u;
+    s_all_done = (input_final && remaining == 0 && n_stop == B); // :414
     uint32_t n_new = min(remaining, n_stop);      // :464
     if (c.simd_pairs) n_new &= ~1u;               // ldpc_decoder_gpu.cpp:623
     s_n_new = s_all_done ? 0u : n_new;
@@ -1339,7 +1381,7 @@ __global__ void __launch_bounds__(kSchedThreads)
     for (uint32_t j = j0; j < j1; ++j) {
       const uint32_t s = virt[j], f = in_gpu[j];
       atomicOr(retire_mask + (s >> 5), 1u << (s & 31u));
-      slot_dst[s].dst_offset = c.results_ring ? uint64_t(j) * c.res_words : uint64_t(f) * c.res_words;
+      slot_dst[s].dst_offset = c.results_ring ? uint64_t(j) * c.res_words : uint64_t(global_frame(c, q, f)) * c.res_words;
       retired_frames[j] = f;
     }
   } else if (n_new > 0) {
@@ -1371,10 +1413,11 @@ __global__ void __launch_bounds__(kSchedThreads)
       const uint32_t s = virt[j], f_old = in_gpu[j], f_new = next + j;
       atomicOr(retire_mask + (s >> 5), 1u << (s & 31u));
       atomicOr(new_mask + (s >> 5), 1u << (s & 31u));
-      slot_dst[s].dst_offset = c.results_ring ? uint64_t(j) * c.res_words : uint64_t(f_old) * c.res_words;
+      slot_dst[s].dst_offset =
+          c.results_ring ? uint64_t(j) * c.res_words : uint64_t(global_frame(c, q, f_old)) * c.res_words;
       retired_frames[j] = f_old;
       slot_entry[s] = j;
-      make_refill_entry(c, f_new, s, entries[j]);
+      make_refill_entry(c, q, f_new, s, entries[j]);
       in_gpu[j] = f_new; // :604-609
       iter_start[f_new] = g;
     }

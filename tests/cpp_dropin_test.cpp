@@ -39,6 +39,21 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < res.size(); ++i) errors += uint64_t(__builtin_popcount(res[i] ^ bits[i]));
     std::printf("frames %u errors %llu iter max/min/avg %u/%u/%.3f\n", n, (unsigned long long)errors, report.max_iter,
                 report.min_iter, report.avg_iter);
+    // extension: one queue of frames through two decoder objects (one per GPU on a multi-GPU box; here both on the
+    // current device), a host thread each and a shared cursor inside the library
+    {
+      ldpc_decoder_gpu dec2(code, channel, sp);
+      ldpc_decoder_gpu *both[2] = {&dec, &dec2};
+      std::vector<uint32_t> res2(res.size(), 0u);
+      test_report report2;
+      ldpc_decoder_gpu::decode_multi(both, 2, dp, n, input.data(), syn.data(), res2.data(), report2);
+      uint64_t errors2 = 0;
+      for (size_t i = 0; i < res2.size(); ++i) errors2 += uint64_t(__builtin_popcount(res2[i] ^ bits[i]));
+      std::printf("multi: frames %llu errors %llu iter max/min/avg %u/%u/%.3f\n",
+                  (unsigned long long)report2.device_report.frames_decoded, (unsigned long long)errors2, report2.max_iter,
+                  report2.min_iter, report2.avg_iter);
+      if (errors2 != 0 || report2.device_report.frames_decoded != n) return 6;
+    }
     // malformed input must surface as the reference's exception type
     try {
       ldpc_code bad("/nonexistent.alist");

@@ -940,3 +940,84 @@ def test_fused_refill_long_rows(monkeypatch):
         assert repa["cn_refill_launches"] > 0
         assert np.array_equal(ia, ib) and np.array_equal(ra, rb_)
         assert harness.count_bit_errors(ra, bits)[ia < 30].sum() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# One frame queue, several decoders (the reference drives device 0 only, h/cuda_manager.h:52)
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+@pytest.mark.parametrize("name,noise,n_frames,log2p,block", [("reg36", 0.78, 230, 5, 7), ("readme13", 0.6, 300, 6, 64),
+                                                             ("tiny", 0.7, 50, 4, 256)])
+def test_queue_with_one_decoder_equals_the_classic_call(small_codes, prec, name, noise, n_frames, log2p, block):
+    """A decoder that draws ALL frames of a queue -- in blocks, reserved as its slots free up -- runs the reference's
+    schedule on frames 0..n-1: results and per-frame iteration counts equal decode()'s bit for bit, whatever the block
+    size (block boundaries inside a staging run, a partial last block, a block larger than the queue)."""
+    gen, path = small_codes[name]
+    fp16 = prec == "fp16"
+    inp, syn, bits, prm = _frames(gen, n_frames, "awgn", noise, 23, np.float16 if fp16 else np.float32)
+    dec = L.Decoder(L.Code(path=path), L.FP16 if fp16 else L.FP32, log2p)
+    res, iters, rep = dec.decode(L.AWGN, prm, inp, syn, num_iter_max=60)
+    for flags in (0, L.FLAG_NO_GRAPH):
+        q = L.FrameQueue(n_frames, block)
+        res2 = np.zeros_like(res)
+        iters2, rep2 = dec.decode_from_queue(q, L.AWGN, prm, inp, syn, res2, num_iter_max=60, flags=flags)
+        q.close()
+        assert rep2["frames_decoded"] == n_frames
+        assert np.array_equal(iters, iters2) and np.array_equal(res, res2)
+        assert (rep2["max_iter"], rep2["min_iter"], rep2["global_iters"]) == (rep["max_iter"], rep["min_iter"], rep["global_iters"])
+
+
+def _check_sharded_against_single(gen, res, iters, res_m, iters_m, imax, k, fp16):
+    """Frames never interact, so a frame decodes the same on whichever device it lands; only its role differs: a frame
+    of a decoder's first batch counts k*j + 1 iterations, a frame loaded later k*j (ldpc_decoder_gpu.cu:306-309)."""
+    assert iters_m.min() > 0                                    # every frame was decoded by somebody
+    diff = np.abs(iters.astype(np.int64) - iters_m.astype(np.int64))
+    assert diff.max() <= k + 1
+    if fp16:
+        assert (diff == 0).mean() > 0.3                         # same role in both runs
+    conv = (iters < imax) & (iters_m < imax)
+    assert conv.mean() > 0.5
+    assert np.array_equal(res[conv], res_m[conv])
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_two_decoders_share_one_queue_on_one_device(small_codes, prec):
+    """ldpc_b200_decode_multi: one host thread per decoder and a shared atomic cursor.  Two decoder objects on the SAME
+    device exercise the whole mechanism (threads, reservations, disjoint result rows, merged report) on a one-GPU box."""
+    gen, path = small_codes["readme13"]
+    fp16 = prec == "fp16"
+    n, imax = 400, 60
+    inp, syn, bits, prm = _frames(gen, n, "awgn", 0.6, 29, np.float16 if fp16 else np.float32)
+    code = L.Code(path=path)
+    a, b = (L.Decoder(code, L.FP16 if fp16 else L.FP32, 5) for _ in range(2))
+    res, iters, rep = a.decode(L.AWGN, prm, inp, syn, num_iter_max=imax)
+    res_m, iters_m, rep_m, per = L.decode_multi([a, b], L.AWGN, prm, inp, syn, num_iter_max=imax, block_frames=16)
+    assert rep_m["frames_decoded"] == n == per[0]["frames_decoded"] + per[1]["frames_decoded"]
+    assert min(p["frames_decoded"] for p in per) >= 32          # both took part
+    _check_sharded_against_single(gen, res, iters, res_m, iters_m, imax, 10, fp16)
+    assert rep_m["max_iter"] == iters_m.max() and rep_m["min_iter"] == iters_m.min()
+    assert rep_m["avg_iter"] == pytest.approx(iters_m.mean(), rel=1e-5)
+    assert harness.count_bit_errors(res_m, bits)[iters_m < imax].sum() == 0
+
+
+def test_two_gpus_share_one_queue():
+    """The same through two DEVICES of one process (skipped on a one-GPU box): the sharded result equals the single-GPU
+    result frame by frame."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_readme_shaped_code(16, seed=1)
+    code = L.Code.from_generated(gen)
+    n, imax = 2048, 80
+    inp, syn, bits, prm = _frames(gen, n, "awgn", 0.8, 31, np.float16)
+    decs = [L.Decoder(code, L.FP16, 8, device=i) for i in range(2)]
+    res, iters, rep = decs[0].decode(L.AWGN, prm, inp, syn, num_iter_max=imax)
+    res_m, iters_m, rep_m, per = L.decode_multi(decs, L.AWGN, prm, inp, syn, num_iter_max=imax)
+    assert rep_m["frames_decoded"] == n and min(p["frames_decoded"] for p in per) >= 256
+    _check_sharded_against_single(gen, res, iters, res_m, iters_m, imax, 10, True)
+    assert harness.count_bit_errors(res_m, bits)[iters_m < imax].sum() == 0
+    # two devices finish the queue faster than one
+    assert rep_m["elapsed_s"] < 0.8 * rep["elapsed_s"]

@@ -195,3 +195,26 @@ def test_fast_cpu_baseline_kernels_agree_with_exact_oracle(small_codes):
     r1, i1, _ = exact.decode(ob.AWGN, prm, 60, 10, inp, syn, simd_pairs=True)
     r2, i2, _ = fast.decode(ob.AWGN, prm, 60, 10, inp, syn, simd_pairs=True)
     assert np.array_equal(i1, i2) and np.array_equal(r1, r2)
+
+
+def test_frame_queue_object_and_shared_memory_cursor():
+    """The shared frame queue (include/ldpc_b200.h) needs no device: private and POSIX-shared-memory flavours, sizes,
+    a second handle on the same shared object, argument checks."""
+    import os
+
+    import ldpc_decoder_b200 as L
+
+    q = L.FrameQueue(1000, 32)
+    assert q.size == 1000
+    q.reset()
+    q.close()
+    name = f"ldpc_b200_test_{os.getpid()}"
+    owner = L.FrameQueue(4096, 64, shm_name=name, create=True)
+    other = L.FrameQueue(shm_name=name, create=False)
+    assert other.size == 4096
+    other.close()
+    owner.close()
+    with pytest.raises(L.LdpcError):
+        L.FrameQueue(shm_name=name, create=False)       # unlinked by its owner
+    with pytest.raises(L.LdpcError):
+        L.FrameQueue(0, 0)
