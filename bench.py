@@ -505,7 +505,7 @@ def main():
             e_elapsed = max_over_ranks(time.perf_counter() - t0)
             barrier()
             frames = sum_over_ranks(float(n_frames * steps))
-            return {"value": frames * gen.n_vars / MBIT / e_elapsed, "unit": "Mb/s",
+            return {"value": frames * gen.n_vars / MBIT / e_elapsed, "unit": "Mb/s", "avg_iter": float(hreps[-1]["avg_iter"]),
                     "h2d_bytes_per_step": int(hreps[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(hreps[-1]["d2h_bytes"]),
                     "ms_per_step": 1e3 * e_elapsed / steps, "steps": steps, "host_frame_pool": pool,
                     "input_row_stride_bytes": pool * s}

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AWGN, BSC, LLR, FP16, FP32, LAYOUT_FRAME_MAJOR, LAYOUT_INTERLEAVED, LAYOUT_PACKED_BITS, FLAG_SIMD_PAIRS, FLAG_TIME_KERNELS, FLAG_NO_GRAPH, FLAG_EARLY_RETIRE, FLAG_HALF_INPUT  # noqa: F401
+from ._lib import AWGN, BSC, LLR, FP16, FP32, LAYOUT_FRAME_MAJOR, LAYOUT_INTERLEAVED, LAYOUT_PACKED_BITS, FLAG_SIMD_PAIRS, FLAG_TIME_KERNELS, FLAG_NO_GRAPH, FLAG_EARLY_RETIRE, FLAG_HALF_INPUT, ORDER_NATURAL, ORDER_LOCALITY  # noqa: F401
 
 
 class LdpcError(RuntimeError):
@@ -39,6 +39,16 @@ def _ptr(a):
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     raise TypeError(type(a))
+
+
+def _wait_for_torch(*buffers):
+    """The library works on the decoder's own (non-blocking) streams; a CUDA tensor torch is still filling on ITS
+    stream (torch.zeros, a copy) must be complete before the library touches it -- the C ABI leaves that to the caller."""
+    for b in buffers:
+        if getattr(b, "is_cuda", False):
+            import torch
+
+            torch.cuda.current_stream(b.device).synchronize()
 
 
 class Code:
@@ -94,6 +104,13 @@ class Code:
     def out_edge_to_var(self):
         return self._arr("out_edge_to_var", self.n_edges)
 
+    def locality_order(self):
+        """(check_order[M], var_order[N]): the storage order a Decoder built with storage_order=ORDER_LOCALITY uses."""
+        co = np.zeros(self.n_checks, dtype=np.uint32)
+        vo = np.zeros(self.n_vars, dtype=np.uint32)
+        _check(_lib.lib().ldpc_b200_code_locality_order(self._h, _ptr(co), _ptr(vo)))
+        return co, vo
+
     def rate(self) -> float:
         return float(np.float32(self.n_vars - self.n_checks) / np.float32(self.n_vars - self.n_erased))
 
@@ -107,9 +124,9 @@ class Decoder:
     """The decoder object (reference ldpc_decoder_gpu / ldpc_decoder_gpu_cuda)."""
 
     def __init__(self, code: Code, precision: int = FP32, max_log2_frames: int = 5, device: int = -1,
-                 mem_headroom_pct: int = 0):
+                 mem_headroom_pct: int = 0, storage_order: int = ORDER_NATURAL):
         cfg = _lib.Config(precision=precision, max_log2_frames=max_log2_frames, device=device,
-                          mem_headroom_pct=mem_headroom_pct)
+                          mem_headroom_pct=mem_headroom_pct, storage_order=storage_order)
         h = C.c_void_p()
         _check(_lib.lib().ldpc_b200_decoder_create(code._h, C.byref(cfg), C.byref(h)))
         self._h = h
@@ -149,6 +166,7 @@ class Decoder:
                                 num_iter_check_parity=num_iter_check_parity, input_layout=layout,
                                 frame_stride=frame_stride, input_pool_frames=pool_frames, flags=flags)
         rep = _lib.Report()
+        _wait_for_torch(inputs, syndromes, results)
         _check(_lib.lib().ldpc_b200_decode(self._h, C.byref(prm), n_frames, _ptr(inputs), _ptr(syndromes),
                                            _ptr(results), C.byref(rep), _ptr(iters)))
         return results, iters, {k: getattr(rep, k) for k, _ in _lib.Report._fields_}
@@ -173,6 +191,7 @@ class Decoder:
                                 frame_stride=frame_stride, input_pool_frames=pool_frames, flags=flags,
                                 queue_lookahead_frames=lookahead)
         rep = _lib.Report()
+        _wait_for_torch(inputs, syndromes, results)
         _check(_lib.lib().ldpc_b200_decode_from_queue(self._h, C.byref(prm), queue._h, _ptr(inputs), _ptr(syndromes),
                                                       _ptr(results), C.byref(rep), _ptr(iter_counts)))
         return iter_counts, {k: getattr(rep, k) for k, _ in _lib.Report._fields_}
@@ -180,6 +199,7 @@ class Decoder:
     def synthesize_frames(self, channel: int, noise: float, start_idx: int, n_frames: int, d_input, d_syndromes,
                           d_ref_bits):
         """Fill CUDA tensors with the reference harness' frames start_idx.. (generated on the device)."""
+        _wait_for_torch(d_input, d_syndromes, d_ref_bits)
         _check(_lib.lib().ldpc_b200_synthesize_frames(self._h, channel, noise, start_idx, n_frames, _ptr(d_input),
                                                       _ptr(d_syndromes), _ptr(d_ref_bits)))
 
@@ -282,6 +302,7 @@ def decode_multi(decoders, channel: int, channel_param: float, inputs, syndromes
     handles = (C.c_void_p * len(decoders))(*[d._h for d in decoders])
     rep = _lib.Report()
     per = (_lib.Report * len(decoders))()
+    _wait_for_torch(inputs, syndromes, results)
     _check(_lib.lib().ldpc_b200_decode_multi(handles, len(decoders), C.byref(prm), n_frames, _ptr(inputs), _ptr(syndromes),
                                              _ptr(results), C.byref(rep), per, _ptr(iters), block_frames))
     as_dict = lambda r: {k: getattr(r, k) for k, _ in _lib.Report._fields_}  # noqa: E731

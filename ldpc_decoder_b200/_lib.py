@@ -19,6 +19,7 @@ FLAG_TIME_KERNELS = 2
 FLAG_NO_GRAPH = 4
 FLAG_EARLY_RETIRE = 8
 FLAG_HALF_INPUT = 16
+ORDER_NATURAL, ORDER_LOCALITY = 0, 1
 
 
 class CodeInfo(C.Structure):
@@ -29,7 +30,7 @@ class CodeInfo(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("precision", C.c_int32), ("max_log2_frames", C.c_uint32), ("device", C.c_int32),
-                ("mem_headroom_pct", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("mem_headroom_pct", C.c_uint32), ("storage_order", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class DecodeParams(C.Structure):
@@ -60,6 +61,7 @@ SYMBOLS = {
     "ldpc_b200_code_destroy": (None, [C.c_void_p]),
     "ldpc_b200_code_get_info": (C.c_int, [C.c_void_p, C.POINTER(CodeInfo)]),
     "ldpc_b200_code_set_erased_vars": (None, [C.c_void_p, C.c_uint32]),
+    "ldpc_b200_code_locality_order": (C.c_int, [C.c_void_p, _U32P, _U32P]),
     "ldpc_b200_decoder_create": (C.c_int, [C.c_void_p, C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "ldpc_b200_decoder_destroy": (None, [C.c_void_p]),
     "ldpc_b200_decoder_frames_in_flight": (C.c_uint32, [C.c_void_p]),

@@ -233,6 +233,12 @@ struct ldpc_b200_decoder {
 
   dev_buf<uint32_t> d_row_ptr, d_col_ptr, d_in_to_out, d_edge_var;
   dev_buf<uint32_t> d_vn_ell; // padded gather list per variable of the variable-node pass (dev::vn_fetch_list)
+  // Locality storage order (ldpc_b200_config::storage_order = 1): message rows, priors, decisions and syndrome rows are
+  // kept in a permuted order; all device tables above are then in STORAGE order and these map original indices to it
+  // (empty / null: identity).  Host copies serve the read-back entry points and the frame synthesis.
+  dev_buf<uint32_t> d_var_pos, d_check_pos, d_row_ptr_orig, d_edge_var_orig;
+  std::vector<uint32_t> h_edge_pos, h_var_pos;
+  bool reordered = false;
   dev_buf<uint8_t> d_msg, d_llr0, d_stage;
   dev_buf<uint32_t> d_syn, d_hard, d_viol, d_stage_syn, d_retire_mask, d_new_mask, d_slot_entry, d_results;
   dev_buf<dev::RefillEntry> d_refill;
@@ -336,7 +342,7 @@ struct ldpc_b200_decoder {
     auto launch = [&](auto kernel, const uint16_t *table) {
       kernel<<<grid_misc, dev::kThreads, 0, stream>>>(msg, l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p,
                                                       d_col_ptr.p, d_in_to_out.p, table, N, n_regular, log2G, channel,
-                                                      param, done_flag(), gate);
+                                                      param, done_flag(), gate, d_var_pos.p);
     };
     // src_kind: dev::kSrcNative / kSrcPackedBits / kSrcHalf (half elements into an fp32 decoder)
     if (precision == LDPC_B200_FP32) {
@@ -359,7 +365,8 @@ struct ldpc_b200_decoder {
     }
     if (with_syndromes)
       dev::refill_syndrome_kernel<<<grid_misc, dev::kThreads, 0, stream>>>(d_syn.p, src_syn, d_refill.p, d_n_new.p,
-                                                                           d_new_mask.p, d_slot_entry.p, M, log2PW);
+                                                                           d_new_mask.p, d_slot_entry.p, M, log2PW,
+                                                                           d_check_pos.p);
   }
   // host-built entries (kernel-level entry points): h_refill[0..n) -> device, then the same kernels
   void launch_refill(uint32_t n_new, const void *src, const uint32_t *src_syn, int channel, float param) {
@@ -385,7 +392,8 @@ struct ldpc_b200_decoder {
     launch_extract_kernel(dst);
   }
   void launch_extract_kernel(uint32_t *dst) { // masks and destinations already on the device
-    dev::extract_kernel<<<grid_misc, 128, 0, stream>>>(d_hard.p, dst, d_retire_mask.p, d_extract.p, W, log2PW);
+    dev::extract_kernel<<<grid_misc, 128, 0, stream>>>(d_hard.p, dst, d_retire_mask.p, d_extract.p, W, log2PW,
+                                                       d_var_pos.p);
   }
 };
 
@@ -486,6 +494,93 @@ ldpc_b200_status select_kernels(ldpc_b200_decoder *d) {
   return LDPC_B200_OK;
 }
 
+// Locality order of checks and variables: Cuthill-McKee breadth-first numbering of the bipartite graph (neighbours
+// by increasing degree, components started from a lowest-degree node), reversed.  Variables whose checks are close
+// get close numbers, so the message rows a variable-node update gathers sit in nearby memory.
+void locality_order(const ldpc_code &code, std::vector<uint32_t> &check_order, std::vector<uint32_t> &var_order) {
+  const uint32_t M = uint32_t(code.n_outputs()), N = uint32_t(code.n_inputs());
+  const std::vector<uint32_t> &rp = code.row_ptr(), &ev = code.out_edge_to_var(), &cp = code.col_ptr(), &i2o = code.in_to_out();
+  std::vector<uint32_t> edge_check(code.n_edges());
+  for (uint32_t c = 0; c < M; ++c)
+    for (uint32_t e = rp[c]; e < rp[c + 1]; ++e) edge_check[e] = c;
+  auto degree = [&](uint32_t node) { return node < M ? rp[node + 1] - rp[node] : cp[node - M + 1] - cp[node - M]; };
+  std::vector<uint32_t> order, by_degree(size_t(M) + N), nb;
+  order.reserve(size_t(M) + N);
+  std::vector<uint8_t> seen(size_t(M) + N, 0);
+  for (uint32_t i = 0; i < M + N; ++i) by_degree[i] = i;
+  std::stable_sort(by_degree.begin(), by_degree.end(), [&](uint32_t a, uint32_t b) { return degree(a) < degree(b); });
+  for (uint32_t start : by_degree) {
+    if (seen[start]) continue;
+    seen[start] = 1;
+    size_t head = order.size();
+    order.push_back(start);
+    while (head < order.size()) {
+      const uint32_t node = order[head++];
+      nb.clear();
+      if (node < M) {
+        for (uint32_t e = rp[node]; e < rp[node + 1]; ++e) nb.push_back(M + ev[e]);
+      } else {
+        const uint32_t v = node - M;
+        for (uint32_t k = cp[v]; k < cp[v + 1]; ++k) nb.push_back(edge_check[i2o[k]]);
+      }
+      std::stable_sort(nb.begin(), nb.end(), [&](uint32_t a, uint32_t b) { return degree(a) < degree(b); });
+      for (uint32_t x : nb)
+        if (!seen[x]) {
+          seen[x] = 1;
+          order.push_back(x);
+        }
+    }
+  }
+  check_order.clear();
+  var_order.clear();
+  for (size_t i = order.size(); i-- > 0;) { // reversed
+    if (order[i] < M) check_order.push_back(order[i]);
+    else var_order.push_back(order[i] - M);
+  }
+}
+
+// The decoder's graph tables in STORAGE order: check_order[c'] / var_order[v'] = original index kept at storage position
+// c' / v'.  Edges keep their order inside a check (check-node sums) and the gather lists keep the original CSC order
+// (variable-node sums), so every floating-point sum is evaluated in the reference's order: results are bit-identical
+// to the natural order, only the memory addresses change.
+struct storage_tables {
+  std::vector<uint32_t> row_ptr, edge_var, col_ptr, in_to_out, edge_pos, var_pos, check_pos;
+};
+storage_tables build_storage_tables(const ldpc_code &code, const std::vector<uint32_t> &check_order,
+                                    const std::vector<uint32_t> &var_order) {
+  const uint32_t M = uint32_t(code.n_outputs()), N = uint32_t(code.n_inputs()), E = code.n_edges();
+  const std::vector<uint32_t> &rp = code.row_ptr(), &ev = code.out_edge_to_var(), &cp = code.col_ptr(), &i2o = code.in_to_out();
+  storage_tables t;
+  t.var_pos.resize(N);
+  t.check_pos.resize(M);
+  for (uint32_t i = 0; i < N; ++i) t.var_pos[var_order[i]] = i;
+  for (uint32_t i = 0; i < M; ++i) t.check_pos[check_order[i]] = i;
+  t.row_ptr.resize(size_t(M) + 1);
+  t.edge_var.resize(E);
+  t.edge_pos.resize(E);
+  uint32_t row = 0;
+  for (uint32_t i = 0; i < M; ++i) {
+    const uint32_t c = check_order[i];
+    t.row_ptr[i] = row;
+    for (uint32_t e = rp[c]; e < rp[c + 1]; ++e) {
+      t.edge_pos[e] = row;
+      t.edge_var[row] = t.var_pos[ev[e]];
+      ++row;
+    }
+  }
+  t.row_ptr[M] = row;
+  t.col_ptr.resize(size_t(N) + 1);
+  t.in_to_out.resize(E);
+  uint32_t k2 = 0;
+  for (uint32_t i = 0; i < N; ++i) {
+    const uint32_t v = var_order[i];
+    t.col_ptr[i] = k2;
+    for (uint32_t k = cp[v]; k < cp[v + 1]; ++k) t.in_to_out[k2++] = t.edge_pos[i2o[k]];
+  }
+  t.col_ptr[N] = k2;
+  return t;
+}
+
 template <typename K> int occupancy_grid(K kernel, int threads, size_t smem, int n_sms, uint64_t items) {
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
@@ -504,10 +599,29 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
                                           ldpc_b200_decoder **out) {
   if (!code_h || !cfg || !out) return fail(LDPC_B200_ERR_INVALID, "null argument");
   *out = nullptr;
-  const ldpc_code &code = *code_h->code;
-  if (code.n_inputs() & 0x1F) // ldpc_decoder_gpu.cu:30-32
+  const ldpc_code &full_code = *code_h->code;
+  if (full_code.n_inputs() & 0x1F) // ldpc_decoder_gpu.cu:30-32
     return fail(LDPC_B200_ERR_MULTIPLE_32, "This decoder only handles input sizes that are multiple of 32");
-  if (!code.structure_ok()) return fail(LDPC_B200_ERR_CODE, "Incorrect code structure\n"); // :40-58
+  if (!full_code.structure_ok()) return fail(LDPC_B200_ERR_CODE, "Incorrect code structure\n"); // :40-58
+  // Erased checks (`#ec=` in the alist header, ldpc_code.cpp:65-69): the LAST n_erased_checks checks carry no target
+  // syndrome bit -- the reference's harness sizes the per-frame syndromes for the effective checks only
+  // (main.cpp:343, n_effective_outputs) while its decoder goes on reading ceil(M/32) words (ldpc_decoder_gpu.cu:104),
+  // i.e. it does not support them.  A check of unknown parity carries no information, so the decoder is built on the
+  // graph WITHOUT those checks, and p_syndromes holds ceil((M - n_erased_checks)/32) words per frame as the harness
+  // allocates them.  Variables left without checks keep their prior.
+  std::unique_ptr<ldpc_code> reduced;
+  if (full_code.n_erased_outputs() > 0) {
+    if (full_code.n_erased_outputs() >= full_code.n_outputs())
+      return fail(LDPC_B200_ERR_INVALID, "every check of the code is erased");
+    const uint32_t m_eff = uint32_t(full_code.n_outputs() - full_code.n_erased_outputs());
+    try {
+      reduced.reset(new ldpc_code(m_eff, uint32_t(full_code.n_inputs()), full_code.row_ptr().data(),
+                                  full_code.out_edge_to_var().data(), uint32_t(full_code.n_erased_inputs())));
+    } catch (const std::exception &e) {
+      return fail(LDPC_B200_ERR_CODE, e.what());
+    }
+  }
+  const ldpc_code &code = reduced ? *reduced : full_code;
   if (cfg->precision != LDPC_B200_FP32 && cfg->precision != LDPC_B200_FP16)
     return fail(LDPC_B200_ERR_INVALID, "unknown precision");
 
@@ -564,10 +678,34 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   CU_TRY(d->d_col_ptr.alloc(d->N + 1));
   CU_TRY(d->d_in_to_out.alloc(d->E));
   CU_TRY(d->d_edge_var.alloc(d->E));
-  CU_TRY(cudaMemcpy(d->d_row_ptr.p, code.row_ptr().data(), 4ull * (d->M + 1), cudaMemcpyHostToDevice));
-  CU_TRY(cudaMemcpy(d->d_col_ptr.p, code.col_ptr().data(), 4ull * (d->N + 1), cudaMemcpyHostToDevice));
-  CU_TRY(cudaMemcpy(d->d_in_to_out.p, code.in_to_out().data(), 4ull * d->E, cudaMemcpyHostToDevice));
-  CU_TRY(cudaMemcpy(d->d_edge_var.p, code.out_edge_to_var().data(), 4ull * d->E, cudaMemcpyHostToDevice));
+  // graph tables, in storage order (identity unless cfg->storage_order asks for the locality order)
+  storage_tables tabs;
+  d->reordered = cfg->storage_order == LDPC_B200_ORDER_LOCALITY;
+  if (cfg->storage_order != LDPC_B200_ORDER_NATURAL && cfg->storage_order != LDPC_B200_ORDER_LOCALITY)
+    return fail(LDPC_B200_ERR_INVALID, "unknown storage_order");
+  if (d->reordered) {
+    std::vector<uint32_t> check_order, var_order;
+    locality_order(code, check_order, var_order);
+    tabs = build_storage_tables(code, check_order, var_order);
+    d->h_edge_pos = tabs.edge_pos;
+    d->h_var_pos = tabs.var_pos;
+    CU_TRY(d->d_var_pos.alloc(d->N));
+    CU_TRY(d->d_check_pos.alloc(d->M));
+    CU_TRY(d->d_row_ptr_orig.alloc(d->M + 1));
+    CU_TRY(d->d_edge_var_orig.alloc(d->E));
+    CU_TRY(cudaMemcpy(d->d_var_pos.p, tabs.var_pos.data(), 4ull * d->N, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d->d_check_pos.p, tabs.check_pos.data(), 4ull * d->M, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d->d_row_ptr_orig.p, code.row_ptr().data(), 4ull * (d->M + 1), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d->d_edge_var_orig.p, code.out_edge_to_var().data(), 4ull * d->E, cudaMemcpyHostToDevice));
+  }
+  const std::vector<uint32_t> &t_row_ptr = d->reordered ? tabs.row_ptr : code.row_ptr();
+  const std::vector<uint32_t> &t_col_ptr = d->reordered ? tabs.col_ptr : code.col_ptr();
+  const std::vector<uint32_t> &t_in_to_out = d->reordered ? tabs.in_to_out : code.in_to_out();
+  const std::vector<uint32_t> &t_edge_var = d->reordered ? tabs.edge_var : code.out_edge_to_var();
+  CU_TRY(cudaMemcpy(d->d_row_ptr.p, t_row_ptr.data(), 4ull * (d->M + 1), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d->d_col_ptr.p, t_col_ptr.data(), 4ull * (d->N + 1), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d->d_in_to_out.p, t_in_to_out.data(), 4ull * d->E, cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d->d_edge_var.p, t_edge_var.data(), 4ull * d->E, cudaMemcpyHostToDevice));
   CU_TRY(d->d_msg.alloc(size_t(d->E) * P * d->elem));
   CU_TRY(d->d_llr0.alloc(size_t(d->N) * P * d->elem));
   CU_TRY(d->d_syn.alloc(size_t(d->M) << d->log2PW));
@@ -646,7 +784,7 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   if (st_sel != LDPC_B200_OK) return st_sel;
   { // gather list of the variable-node pass: [degree, rows of the first D edges (CSC order), ..., col_ptr[v]] per variable
     const int D = d->deg_vn == 4 ? 4 : (d->deg_vn == 6 ? 6 : 8), W = D <= 6 ? 8 : 12; // as select_for_precision
-    const std::vector<uint32_t> &cp = code.col_ptr(), &i2o = code.in_to_out();
+    const std::vector<uint32_t> &cp = t_col_ptr, &i2o = t_in_to_out; // storage order
     std::vector<uint32_t> ell(size_t(d->N) * W, 0u);
     for (uint32_t v = 0; v < d->N; ++v) {
       uint32_t *e = &ell[size_t(v) * W];
@@ -673,6 +811,15 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   d->grid_misc = d->n_sms * 8; // x 256 threads: a multiple of every row length G <= 2048 (refill_kernel keeps its g)
   CU_TRY(cudaStreamSynchronize(d->stream));
   *out = d.release();
+  return LDPC_B200_OK;
+}
+
+ldpc_b200_status ldpc_b200_code_locality_order(const ldpc_b200_code *code, uint32_t *check_order, uint32_t *var_order) {
+  if (!code || !check_order || !var_order) return fail(LDPC_B200_ERR_INVALID, "null argument");
+  std::vector<uint32_t> co, vo;
+  locality_order(*code->code, co, vo);
+  std::copy(co.begin(), co.end(), check_order);
+  std::copy(vo.begin(), vo.end(), var_order);
   return LDPC_B200_OK;
 }
 
@@ -1719,7 +1866,9 @@ ldpc_b200_status ldpc_b200_debug_check(ldpc_b200_decoder *d, uint8_t *violated) 
   return LDPC_B200_OK;
 }
 
-static ldpc_b200_status read_column(ldpc_b200_decoder *d, const uint8_t *src, uint64_t rows, uint32_t slot, float *out) {
+// pos: storage row of each original row (null: identity)
+static ldpc_b200_status read_column(ldpc_b200_decoder *d, const uint8_t *src, uint64_t rows, uint32_t slot, float *out,
+                                    const std::vector<uint32_t> *pos = nullptr) {
   if (slot >= d->P) return fail(LDPC_B200_ERR_INVALID, "slot out of range");
   CU_TRY(cudaSetDevice(d->device));
   dev_buf<uint8_t> tmp;
@@ -1735,23 +1884,25 @@ static ldpc_b200_status read_column(ldpc_b200_decoder *d, const uint8_t *src, ui
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaMemcpyAsync(host.data(), tmp.p, rows * d->elem, cudaMemcpyDeviceToHost, d->stream));
   CU_TRY(cudaStreamSynchronize(d->stream));
+  const bool perm = pos && !pos->empty();
   if (d->elem == 4) {
-    memcpy(out, host.data(), rows * 4);
+    const float *f = reinterpret_cast<const float *>(host.data());
+    for (uint64_t i = 0; i < rows; ++i) out[i] = f[perm ? (*pos)[i] : i];
   } else {
     const __half *h = reinterpret_cast<const __half *>(host.data());
-    for (uint64_t i = 0; i < rows; ++i) out[i] = __half2float(h[i]);
+    for (uint64_t i = 0; i < rows; ++i) out[i] = __half2float(h[perm ? (*pos)[i] : i]);
   }
   return LDPC_B200_OK;
 }
 
 ldpc_b200_status ldpc_b200_debug_read_messages(ldpc_b200_decoder *d, uint32_t slot, float *out_e) {
   if (!d || !out_e) return fail(LDPC_B200_ERR_INVALID, "null argument");
-  return read_column(d, d->d_msg.p, d->E, slot, out_e);
+  return read_column(d, d->d_msg.p, d->E, slot, out_e, &d->h_edge_pos);
 }
 
 ldpc_b200_status ldpc_b200_debug_read_priors(ldpc_b200_decoder *d, uint32_t slot, float *out_n) {
   if (!d || !out_n) return fail(LDPC_B200_ERR_INVALID, "null argument");
-  return read_column(d, d->d_llr0.p, d->N, slot, out_n);
+  return read_column(d, d->d_llr0.p, d->N, slot, out_n, &d->h_var_pos);
 }
 
 ldpc_b200_status ldpc_b200_debug_read_hard(ldpc_b200_decoder *d, uint32_t slot, uint32_t *out_words) {
@@ -1792,8 +1943,10 @@ ldpc_b200_status ldpc_b200_synthesize_frames(ldpc_b200_decoder *d, int32_t chann
     dev::synth_noise_kernel<__half><<<(n_frames + 63) / 64, 64, 0, d->stream>>>(
         sliced.p, static_cast<__half *>(d_input), d_ref_bits, start_idx, n_frames, d->N, n_tx, n_groups, channel, noise);
   const uint64_t n_syn = uint64_t(d->M) * n_groups;
-  dev::synth_syndrome_kernel<<<unsigned((n_syn + 255) / 256), 256, 0, d->stream>>>(sliced.p, syn_sliced.p, d->d_row_ptr.p,
-                                                                                 d->d_edge_var.p, d->M, n_groups);
+  // the syndromes are those of the code as given: original check and variable numbering
+  dev::synth_syndrome_kernel<<<unsigned((n_syn + 255) / 256), 256, 0, d->stream>>>(
+      sliced.p, syn_sliced.p, d->reordered ? d->d_row_ptr_orig.p : d->d_row_ptr.p,
+      d->reordered ? d->d_edge_var_orig.p : d->d_edge_var.p, d->M, n_groups);
   const uint64_t n_warps = uint64_t(d->S) * n_groups;
   dev::synth_syndrome_transpose_kernel<<<unsigned((n_warps * 32 + 255) / 256), 256, 0, d->stream>>>(
       syn_sliced.p, d_syndromes, d->M, n_groups, n_frames, d->S);

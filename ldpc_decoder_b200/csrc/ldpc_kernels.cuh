@@ -35,6 +35,9 @@ namespace dev {
 #ifndef LDPC_HMIN_CLAMP
 #define LDPC_HMIN_CLAMP 1 // fp16 table index: packed-half clamp + byte offsets (A/B on B200: CN +2.4 %, VN +5.1 %)
 #endif
+#ifndef LDPC_REFILL_UNROLL
+#define LDPC_REFILL_UNROLL 4 // variables per loop trip of the priors-only refill kernel
+#endif
 #ifndef LDPC_MERGE_DECISION_STORES
 #define LDPC_MERGE_DECISION_STORES 1 // variable-node pass with decisions: one 32-bit store per 32 slots (see vn_update_kernel)
 #endif
@@ -895,7 +898,10 @@ __global__ void __launch_bounds__(kThreads)
                   const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
                   const uint32_t *__restrict__ col_ptr, const uint32_t *__restrict__ in_to_out,
                   const uint16_t *__restrict__ phi_table, uint32_t n_vars, uint32_t n_regular, uint32_t log2_g,
-                  int channel, float param, const uint32_t *__restrict__ ctl, uint32_t gate) {
+                  int channel, float param, const uint32_t *__restrict__ ctl, uint32_t gate,
+                  const uint32_t *__restrict__ var_pos) {
+  // var_pos: storage row of each variable when the decoder keeps its arrays in a locality order (nullptr: identity);
+  // col_ptr / in_to_out are then the storage-order tables
   constexpr bool packed_bits = kSrc == kSrcPackedBits;
   static_assert(kSrc != kSrcHalf || Tr::kFramesPerVec == 4, "half transfer elements are widened by fp32 decoders only");
   if (*n_new_ptr == 0) return; // written by the scheduler kernel (or the host for kernel-level calls)
@@ -922,46 +928,66 @@ __global__ void __launch_bounds__(kThreads)
   }
 #pragma unroll
   for (int w = 0; w < 4; ++w) word(SEL, w) = Tr::lane_mask(nm >> (w * Tr::kFramesPerWord));
-  for (uint64_t item = first; item < total; item += uint64_t(gridDim.x) * blockDim.x) {
-    const uint32_t i = uint32_t(item >> log2_g);
-    uint4 L = make_uint4(0, 0, 0, 0), O = make_uint4(0, 0, 0, 0);
-    if (i < n_regular) {
-      const uint64_t at_i = uint64_t(i) * src_stride;
+  // kUnroll variables per trip (priors-only variant): the loads of a trip are independent, a thread's trips are not, and
+  // with only ~1800 trips per thread the launch was latency-bound at one variable per trip
+  constexpr int kUnroll = kMsgRows ? 1 : LDPC_REFILL_UNROLL;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t item = first; item < total; item += kUnroll * stride) {
+    uint4 L[kUnroll], old[kUnroll];
+    uint32_t iv[kUnroll], vrow[kUnroll];
+    bool valid[kUnroll];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        if ((nm >> j) & 1u) {
-          // packed hard-decision input (1 bit per transmitted variable, frame-major words): bit 1 <-> +1
-          uint32_t pbit = 0;
-          if (packed_bits) pbit = (__ldg(static_cast<const uint32_t *>(src) + off[j] + (i >> 5)) >> (i & 31u)) & 1u;
-          if (V == 4) {
-            uint32_t raw;
-            if (packed_bits) raw = pbit ? 0x3F800000u : 0xBF800000u;
-            else if (kSrc == kSrcHalf)
-              raw = __float_as_uint(__half2float(__ushort_as_half(__ldg(static_cast<const uint16_t *>(src) + off[j] + at_i))));
-            else raw = __ldg(static_cast<const uint32_t *>(src) + off[j] + at_i);
-            word(L, j & 3) = TraitsF32::to_llr(raw, channel, param);
-          } else {
-            const uint32_t raw = TraitsF16::to_llr(packed_bits ? uint16_t(pbit ? 0x3C00u : 0xBC00u)
-                                                               : __ldg(static_cast<const uint16_t *>(src) + off[j] + at_i),
-                                                   channel, param);
-            word(L, (j >> 1) & 3) |= raw << ((j & 1) * 16);
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint64_t it = item + uint64_t(u) * stride;
+      valid[u] = it < total;
+      iv[u] = uint32_t(it >> log2_g);
+      vrow[u] = (valid[u] && var_pos) ? __ldg(var_pos + iv[u]) : iv[u];
+      old[u] = make_uint4(0, 0, 0, 0);
+      if (valid[u] && nm != kFull) old[u] = ld_stream(llr0 + (size_t(vrow[u]) << log2_g) + g);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = iv[u];
+      L[u] = make_uint4(0, 0, 0, 0);
+      if (valid[u] && i < n_regular) {
+        const uint64_t at_i = uint64_t(i) * src_stride;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          if ((nm >> j) & 1u) {
+            // packed hard-decision input (1 bit per transmitted variable, frame-major words): bit 1 <-> +1
+            uint32_t pbit = 0;
+            if (packed_bits) pbit = (__ldg(static_cast<const uint32_t *>(src) + off[j] + (i >> 5)) >> (i & 31u)) & 1u;
+            if (V == 4) {
+              uint32_t raw;
+              if (packed_bits) raw = pbit ? 0x3F800000u : 0xBF800000u;
+              else if (kSrc == kSrcHalf)
+                raw = __float_as_uint(__half2float(__ushort_as_half(__ldg(static_cast<const uint16_t *>(src) + off[j] + at_i))));
+              else raw = __ldg(static_cast<const uint32_t *>(src) + off[j] + at_i);
+              word(L[u], j & 3) = TraitsF32::to_llr(raw, channel, param);
+            } else {
+              const uint32_t raw = TraitsF16::to_llr(packed_bits ? uint16_t(pbit ? 0x3C00u : 0xBC00u)
+                                                                 : __ldg(static_cast<const uint16_t *>(src) + off[j] + at_i),
+                                                     channel, param);
+              word(L[u], (j >> 1) & 3) |= raw << ((j & 1) * 16);
+            }
           }
         }
       }
     }
-    {
-      uint4 *p = llr0 + (size_t(i) << log2_g) + g;
-      uint4 old = make_uint4(0, 0, 0, 0);
-      if (nm != kFull) old = ld_stream(p);
 #pragma unroll
-      for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(L, w);
-      st_stream(p, old);
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!valid[u]) continue;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) word(old[u], w) = (word(old[u], w) & ~word(SEL, w)) | word(L[u], w);
+      st_stream(llr0 + (size_t(vrow[u]) << log2_g) + g, old[u]);
     }
     if (kMsgRows) {
       // start messages: phi_abs(|prior|) with the prior's sign (punctured variables: phi_abs(0))
+      const uint32_t i = vrow[0];
+      uint4 O = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        const uint32_t lw = word(L, w);
+        const uint32_t lw = word(L[0], w);
         uint32_t r;
         if (V == 4) r = __float_as_uint(phi_abs_f32(__uint_as_float(lw & 0x7FFFFFFFu)));
         else r = uint32_t(__ldg(phi_table + (lw & 0x7FFFu))) | (uint32_t(__ldg(phi_table + ((lw >> 16) & 0x7FFFu))) << 16);
@@ -970,11 +996,11 @@ __global__ void __launch_bounds__(kThreads)
       const uint32_t a = __ldg(col_ptr + i), b = __ldg(col_ptr + i + 1);
       for (uint32_t ie = a; ie < b; ++ie) {
         uint4 *p = msg + (size_t(__ldg(in_to_out + ie)) << log2_g) + g;
-        uint4 old = make_uint4(0, 0, 0, 0);
-        if (nm != kFull) old = ld_stream(p);
+        uint4 oldm = make_uint4(0, 0, 0, 0);
+        if (nm != kFull) oldm = ld_stream(p);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(O, w);
-        st_stream(p, old);
+        for (int w = 0; w < 4; ++w) word(oldm, w) = (word(oldm, w) & ~word(SEL, w)) | word(O, w);
+        st_stream(p, oldm);
       }
     }
   }
@@ -989,7 +1015,7 @@ __global__ void __launch_bounds__(kThreads)
     refill_syndrome_kernel(uint32_t *__restrict__ syn, const uint32_t *__restrict__ src_syn,
                            const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
                            const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
-                           uint32_t n_checks, uint32_t log2_pw) {
+                           uint32_t n_checks, uint32_t log2_pw, const uint32_t *__restrict__ check_pos) {
   if (*n_new_ptr == 0) return;
   constexpr int kBatch = 8;
   const uint32_t PW = 1u << log2_pw;
@@ -1016,7 +1042,7 @@ __global__ void __launch_bounds__(kThreads)
         }
       }
       for (uint32_t cc = 0; cc < cn; ++cc) {
-        uint32_t *p = syn + (size_t(c0 + cc) << log2_pw) + w;
+        uint32_t *p = syn + (size_t(check_pos ? __ldg(check_pos + c0 + cc) : c0 + cc) << log2_pw) + w;
         uint32_t x = *p & ~batch_mask;
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) x |= ((src[j] >> cc) & 1u) << pos[j]; // unused entries: src = 0
@@ -1036,7 +1062,8 @@ struct ExtractEntry {
 
 __global__ void __launch_bounds__(128)
     extract_kernel(const uint32_t *__restrict__ hard, uint32_t *__restrict__ dst, const uint32_t *__restrict__ retire_mask,
-                   const ExtractEntry *__restrict__ slot_dst, uint32_t n_words /* N/32 */, uint32_t log2_pw) {
+                   const ExtractEntry *__restrict__ slot_dst, uint32_t n_words /* N/32 */, uint32_t log2_pw,
+                   const uint32_t *__restrict__ var_pos) {
   __shared__ uint32_t s_out[4][32][33];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t PW = 1u << log2_pw;
@@ -1050,7 +1077,8 @@ __global__ void __launch_bounds__(128)
     const uint32_t j0 = tile << 5;
     const uint32_t jn = min(32u, n_words - j0);
     for (uint32_t jj = 0; jj < jn; ++jj) {
-      const uint32_t x = __ldg(hard + ((size_t(j0 + jj) * 32 + lane) << log2_pw) + w);
+      const uint32_t var = (j0 + jj) * 32 + lane;
+      const uint32_t x = __ldg(hard + (size_t(var_pos ? __ldg(var_pos + var) : var) << log2_pw) + w);
       uint32_t mm = mask, k = 0;
       while (mm) {
         const uint32_t bit = __ffs(mm) - 1;

@@ -389,6 +389,7 @@ def _synth(dec, channel, noise, start, n, gen, fp16):
     d_in = torch.zeros((N, n), dtype=torch.float16 if fp16 else torch.float32, device="cuda")
     d_syn = torch.zeros((n, (M + 31) // 32), dtype=torch.int32, device="cuda")
     d_ref = torch.zeros((n, N // 32), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()  # torch fills on its own stream; the library works on the decoder's stream
     dec.synthesize_frames(L.BSC if channel == "bsc" else L.AWGN, noise, start, n, d_in, d_syn, d_ref)
     return d_in, d_syn, d_ref
 
@@ -738,6 +739,7 @@ def test_on_device_frame_synthesis_matches_the_cpu_generator(small_codes, prec, 
     d_in = torch.zeros((N, n), dtype=torch.float16 if fp16 else torch.float32, device="cuda")
     d_syn = torch.zeros((n, S), dtype=torch.int32, device="cuda")
     d_ref = torch.zeros((n, W), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()  # torch fills on its own stream; the library works on the decoder's stream
     dec.synthesize_frames(L.BSC if channel == "bsc" else L.AWGN, noise, start, n, d_in, d_syn, d_ref)
     assert np.array_equal(d_ref.cpu().numpy().view(np.uint32), ref)
     assert np.array_equal(d_syn.cpu().numpy().view(np.uint32), syn)
@@ -940,6 +942,94 @@ def test_fused_refill_long_rows(monkeypatch):
         assert repa["cn_refill_launches"] > 0
         assert np.array_equal(ia, ib) and np.array_equal(ra, rb_)
         assert harness.count_bit_errors(ra, bits)[ia < 30].sum() == 0
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+@pytest.mark.parametrize("name", ["readme13", "hideg", "tiny", "scrambled_band"])
+def test_locality_storage_order_is_bit_exact(small_codes, prec, name):
+    """SURVEY row f4 inside the decoder: LDPC_B200_ORDER_LOCALITY stores checks and variables in a Cuthill-McKee order
+    (message rows of a variable close together) while every sum keeps the reference's order (in-edge order of
+    ldpc_code.cpp:139-151).  Priors, messages after several iterations, decisions, violation flags, decode() results
+    and iteration counts are identical to the natural order bit for bit -- in BOTH precisions."""
+    from ldpc_decoder_b200 import alist
+
+    if name == "scrambled_band":  # a banded (3,6) code whose rows and columns were shuffled: locality to recover
+        rng = np.random.default_rng(5)
+        n, win = 4096, 96
+        sockets = np.repeat(np.arange(n, dtype=np.int64), 3)
+        for b in range(0, sockets.size, win):
+            blk = sockets[b:b + win]
+            sockets[b:b + win] = blk[rng.permutation(blk.size)]
+        m = n // 2
+        band = alist.Code(m, n, np.arange(0, 6 * m + 1, 6, dtype=np.uint32), sockets.astype(np.uint32), 0)
+        vperm, cperm = rng.permutation(n), rng.permutation(m)
+        rows = [vperm[band.col_idx[band.row_ptr[c]:band.row_ptr[c + 1]]] for c in cperm]
+        gen = alist.Code(m, n, band.row_ptr, np.concatenate(rows).astype(np.uint32), 0)
+    else:
+        gen, _ = small_codes[name]
+    fp16 = prec == "fp16"
+    code = L.Code.from_generated(gen)
+    channel, noise = ("bsc", 0.01) if name == "hideg" else ("awgn", 0.7)
+    ch = L.BSC if channel == "bsc" else L.AWGN
+    inp, syn, bits, prm = _frames(gen, 200, channel, noise, 41, np.float16 if fp16 else np.float32)
+    n_reg = gen.n_vars - gen.n_erased
+    a = L.Decoder(code, L.FP16 if fp16 else L.FP32, 5)
+    b = L.Decoder(code, L.FP16 if fp16 else L.FP32, 5, storage_order=L.ORDER_LOCALITY)
+    for d in (a, b):
+        d.refill(ch, prm, inp[:n_reg, :32], syn[:32])
+        d.iterate(7, final_bits=True)
+    for s in (0, 5, 31):
+        assert np.array_equal(a.priors(s).view(np.uint32), b.priors(s).view(np.uint32)), s
+        assert np.array_equal(a.messages(s).view(np.uint32), b.messages(s).view(np.uint32)), s
+        assert np.array_equal(a.hard(s), b.hard(s)), s
+    assert np.array_equal(a.check(), b.check())
+    for flags in (0, L.FLAG_EARLY_RETIRE):
+        ra, ia, _ = a.decode(ch, prm, inp, syn, num_iter_max=50, flags=flags)
+        rb_, ib, _ = b.decode(ch, prm, inp, syn, num_iter_max=50, flags=flags)
+        assert np.array_equal(ia, ib) and np.array_equal(ra, rb_)
+    # frames synthesized on the device are those of the code as given, whatever the storage order
+    import torch
+
+    N, M = gen.n_vars, gen.n_checks
+    outs = []
+    for d in (a, b):
+        d_in = torch.zeros((N, 40), dtype=torch.float16 if fp16 else torch.float32, device="cuda")
+        d_syn = torch.zeros((40, (M + 31) // 32), dtype=torch.int32, device="cuda")
+        d_ref = torch.zeros((40, N // 32), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        d.synthesize_frames(ch, 0.01 if channel == "bsc" else 0.7, 99, 40, d_in, d_syn, d_ref)
+        outs.append((d_in.cpu().numpy(), d_syn.cpu().numpy(), d_ref.cpu().numpy()))
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_erased_checks_header_is_honoured(small_codes, prec):
+    """`#ec=k` (ldpc_code.cpp:65-69; parsed by the reference, used by its harness to size the syndromes, main.cpp:343,
+    but not by its decoder): the last k checks carry no target syndrome bit.  The decoder is built on the graph without
+    them and takes ceil((M-k)/32) syndrome words per frame: identical, bit for bit, to decoding the code whose last k
+    checks were removed."""
+    from ldpc_decoder_b200 import alist
+
+    gen, _ = small_codes["readme13"]
+    k = 100
+    fp16 = prec == "fp16"
+    m_eff = gen.n_checks - k
+    e_eff = int(gen.row_ptr[m_eff])
+    cut = alist.Code(m_eff, gen.n_vars, gen.row_ptr[: m_eff + 1], gen.col_idx[:e_eff], gen.n_erased)
+    text = "#ec=%d\n" % k + alist.alist_text(gen)
+    code_ec = L.Code(text=text)
+    assert code_ec.n_erased_checks == k and code_ec.n_checks == gen.n_checks
+    inp, syn, bits, prm = _frames(cut, 120, "awgn", 0.5, 3, np.float16 if fp16 else np.float32)
+    assert syn.shape[1] == (m_eff + 31) // 32
+    a = L.Decoder(code_ec, L.FP16 if fp16 else L.FP32, 5)
+    b = L.Decoder(L.Code.from_generated(cut), L.FP16 if fp16 else L.FP32, 5)
+    ra, ia, _ = a.decode(L.AWGN, prm, inp, syn, num_iter_max=60)
+    rb_, ib, _ = b.decode(L.AWGN, prm, inp, syn, num_iter_max=60)
+    assert np.array_equal(ra, rb_) and np.array_equal(ia, ib)
+    conv = ia < 60
+    assert conv.mean() > 0.8
+    assert np.array_equal(cut.syndrome_packed(ra[conv]), syn[conv])
 
 
 # ---------------------------------------------------------------------------------------------------------------

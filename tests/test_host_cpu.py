@@ -218,3 +218,36 @@ def test_frame_queue_object_and_shared_memory_cursor():
         L.FrameQueue(shm_name=name, create=False)       # unlinked by its owner
     with pytest.raises(L.LdpcError):
         L.FrameQueue(0, 0)
+
+
+def test_locality_storage_order_recovers_hidden_locality():
+    """The in-decoder storage order (LDPC_B200_ORDER_LOCALITY) is a permutation of checks and of
+    variables, and on a banded code whose rows and columns were shuffled it brings the message rows a variable gathers
+    back together (mean span of a variable's rows, in storage rows)."""
+    import ldpc_decoder_b200 as L
+    from ldpc_decoder_b200 import alist
+
+    rng = np.random.default_rng(5)
+    n, win = 8192, 96
+    sockets = np.repeat(np.arange(n, dtype=np.int64), 3)
+    for b in range(0, sockets.size, win):
+        blk = sockets[b:b + win]
+        sockets[b:b + win] = blk[rng.permutation(blk.size)]
+    m = n // 2
+    band = alist.Code(m, n, np.arange(0, 6 * m + 1, 6, dtype=np.uint32), sockets.astype(np.uint32), 0)
+    vperm, cperm = rng.permutation(n), rng.permutation(m)
+    rows = [vperm[band.col_idx[band.row_ptr[c]:band.row_ptr[c + 1]]] for c in cperm]
+    gen = alist.Code(m, n, band.row_ptr, np.concatenate(rows).astype(np.uint32), 0)
+    co, vo = L.Code.from_generated(gen).locality_order()
+    assert np.array_equal(np.sort(co), np.arange(m)) and np.array_equal(np.sort(vo), np.arange(n))
+
+    def mean_span(check_order):
+        pos = np.empty(m, dtype=np.int64)
+        pos[check_order] = np.arange(m)
+        check_of_edge = np.repeat(pos, 6)                 # storage position of each edge's check (6 rows per check)
+        order = np.argsort(gen.col_idx, kind="stable")
+        per_var = check_of_edge[order].reshape(n, 3)
+        return float((per_var.max(axis=1) - per_var.min(axis=1)).mean()) * 6
+
+    before, after = mean_span(np.arange(m)), mean_span(co.astype(np.int64))
+    assert after < before / 20, (before, after)
