@@ -508,6 +508,9 @@ def main():
             return {"value": frames * gen.n_vars / MBIT / e_elapsed, "unit": "Mb/s", "avg_iter": float(hreps[-1]["avg_iter"]),
                     "h2d_bytes_per_step": int(hreps[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(hreps[-1]["d2h_bytes"]),
                     "ms_per_step": 1e3 * e_elapsed / steps, "steps": steps, "host_frame_pool": pool,
+                    "host_stage_s_per_step": float(np.mean([r["host_stage_s"] for r in hreps])),
+                    "first_batch_stage_s": float(np.mean([r["first_batch_stage_s"] for r in hreps])),
+                    "device_s_per_step": float(np.mean([r["device_s"] for r in hreps])),
                     "input_row_stride_bytes": pool * s}
 
         e2e = e2e_leg(inp_host, syn_host, args.pool, args.steps)
@@ -555,6 +558,25 @@ def main():
             del d_res_q
             torch.cuda.empty_cache()
 
+    # EXTENSION, not the reference's end-of-input behaviour: frames retire when they stop once the
+    # input is exhausted and the survivors are compacted -- reported beside the headline, never as the headline
+    early = None
+    if not args.skip_extra and not args.early_retire:
+        def step_early():
+            return dec.decode(L.AWGN, prm, d_in, d_syn, n_frames=n_frames, results=d_res, pool_frames=args.pool,
+                              flags=L.FLAG_EARLY_RETIRE, **common)
+        step_early()
+        barrier()
+        t0 = time.perf_counter()
+        _, it_e, rep_e = step_early()
+        torch.cuda.synchronize()
+        e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        early = {"flag": "LDPC_B200_FLAG_EARLY_RETIRE", "value": sum_over_ranks(float(n_frames)) * gen.n_vars / MBIT / e_s,
+                 "unit": "Mb/s", "ms_per_step": 1e3 * e_s, "steps": 1,
+                 "slot_iterations_vs_reference_schedule": rep_e["slot_iterations"] / float(reps[-1]["slot_iterations"]),
+                 "iteration_counts_identical": bool(np.array_equal(it_e, iters))}
+
     cpu = ref_cuda = others = None
     if rank == 0 and world == 1:
         if not args.skip_cpu:
@@ -589,7 +611,7 @@ def main():
             "frames_checked": int(conv.sum()), "converged_frames_equal_transmitted_words": words_ok,
             "syndromes_satisfied": ok, "frac_converged": float(conv.mean()),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_small_pool": e2e_small,
-            "ref_cuda_build": ref_cuda, "other_configs": others, "shared_queue": shared,
+            "ref_cuda_build": ref_cuda, "other_configs": others, "shared_queue": shared, "extension_early_retire": early,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         line["value_over_roofline"] = line["value"] / line["roofline_mbps"]

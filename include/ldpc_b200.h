@@ -178,6 +178,10 @@ typedef struct ldpc_b200_report {
   uint64_t cn_refill_launches;
   double cn_refill_s;
   uint64_t frames_decoded; /* frames this call decoded (n_frames; less for a decoder sharing a queue with others) */
+  /* host-resident buffers: wall time the calling thread spent gathering frames into the pinned staging mirror and   *
+   * enqueueing their H2D copies (the reference's prepare_vectors + transfer_vectors), and the part of it that came    *
+   * before the first kernel could start (the first batch)                                                            */
+  double host_stage_s, first_batch_stage_s;
 } ldpc_b200_report;
 
 /* decode() (ldpc_decoder_gpu.h:102-110; semantics of ldpc_decoder_gpu.cu:283-634).

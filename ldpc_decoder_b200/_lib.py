@@ -49,7 +49,7 @@ class Report(C.Structure):
                 ("check_s", C.c_double), ("retire_s", C.c_double), ("refill_s", C.c_double),
                 ("frames_refilled", C.c_uint64), ("graph_launches", C.c_uint64),
                 ("slot_iterations", C.c_uint64), ("cn_refill_launches", C.c_uint64), ("cn_refill_s", C.c_double),
-                ("frames_decoded", C.c_uint64)]
+                ("frames_decoded", C.c_uint64), ("host_stage_s", C.c_double), ("first_batch_stage_s", C.c_double)]
 
 
 # every symbol include/ldpc_b200.h declares: name -> (restype, argtypes)

@@ -275,16 +275,26 @@ struct ldpc_b200_decoder {
 
   // Staging for host-resident buffers is allocated on first use: a decoder fed from device memory never pays for
   // the pinned mirror (N*P*s bytes) nor the device ring.
-  ldpc_b200_status ensure_input_staging() {
-    const size_t P_ = P;
-    if (!d_stage.p) CU_TRY(d_stage.alloc(size_t(N) * P_ * elem));
-    if (!h_stage.p) CU_TRY(h_stage.alloc(size_t(N) * P_ * elem));
+  // ring_frames: frame positions of the staging ring (P plus the look-ahead slack of host-fed calls, stage_slack)
+  ldpc_b200_status ensure_input_staging(uint32_t ring_frames = 0) {
+    const size_t need = size_t(N) * std::max<size_t>(P, ring_frames) * elem;
+    if (!d_stage.p || d_stage.n < need) CU_TRY(d_stage.alloc(need));
+    if (!h_stage.p || h_stage.n < need) CU_TRY(h_stage.alloc(need));
     return LDPC_B200_OK;
   }
-  ldpc_b200_status ensure_syndrome_staging() {
-    if (!d_stage_syn.p) CU_TRY(d_stage_syn.alloc(size_t(S) * P));
-    if (!h_stage_syn.p) CU_TRY(h_stage_syn.alloc(size_t(S) * P));
+  ldpc_b200_status ensure_syndrome_staging(uint32_t ring_frames = 0) {
+    const size_t need = size_t(S) * std::max<size_t>(P, ring_frames);
+    if (!d_stage_syn.p || d_stage_syn.n < need) CU_TRY(d_stage_syn.alloc(need));
+    if (!h_stage_syn.p || h_stage_syn.n < need) CU_TRY(h_stage_syn.alloc(need));
     return LDPC_B200_OK;
+  }
+  // Host-fed calls stage frames in passes of several hundred frames instead of one pass per check period: the ring
+  // holds frames_in_flight + slack frames; a pass is started when fewer than a quarter of the slack is staged beyond
+  // what the next check may need, and fills the slack.  Each pass then reads kilobyte runs of every row of the caller's
+  // strided array instead of the ~900 bytes a single period consumes (fewer page walks and DRAM streams per frame).
+  uint32_t stage_slack_pct = 50; // LDPC_B200_STAGE_SLACK_PCT
+  uint32_t stage_slack(uint32_t batch, uint32_t ring_block) const {
+    return uint32_t(uint64_t(batch) * stage_slack_pct / 100) / ring_block * ring_block;
   }
   ldpc_b200_status ensure_result_staging() {
     if (!d_results.p) CU_TRY(d_results.alloc(size_t(W) * P));
@@ -308,8 +318,10 @@ struct ldpc_b200_decoder {
   int fused_mode = -1; // fused refill: -1 chosen per check period on the device, 0 never, 1 always (LDPC_B200_FUSED_REFILL)
   uint32_t fused_min_pct = 6; // -1 mode: a period fuses when it loads at least this share of the slots (LDPC_B200_FUSED_MIN_PCT)
   int threads_cn = dev::kThreads, threads_vn = dev::kThreads;
-  bool cn_bulk = false;   // experiment (LDPC_B200_CN_BULK=1): bulk-async staged check-node kernel
+  bool cn_bulk = false;   // bulk-async (TMA) staged check-node kernel (LDPC_B200_CN_BULK)
+  bool vn_bulk = false;   // bulk-async (TMA) staged variable-node kernel (LDPC_B200_VN_BULK)
   size_t smem_cn = 0;     // dynamic shared memory of the check-node kernel
+  size_t smem_vn = 0;     // ... of the variable-node kernel
   // gate (dev::kGate*): run always / only in a period whose refill is fused / only in a period whose refill is not
   void launch_cn(uint32_t gate = dev::kGateNone) {
     k_cn<<<grid_cn, threads_cn, smem_cn, stream>>>(reinterpret_cast<uint4 *>(d_msg.p), d_row_ptr.p,
@@ -325,7 +337,7 @@ struct ldpc_b200_decoder {
         tab_last, M, log2G, done_flag(), ra, gate);
   }
   void launch_vn(bool bits) {
-    (bits ? k_vnb : k_vn)<<<bits ? grid_vnb : grid_vn, threads_vn, smem_tab, stream>>>(
+    (bits ? k_vnb : k_vn)<<<bits ? grid_vnb : grid_vn, threads_vn, smem_vn, stream>>>(
         reinterpret_cast<uint4 *>(d_msg.p), reinterpret_cast<const uint4 *>(d_llr0.p), d_vn_ell.p, d_in_to_out.p,
         reinterpret_cast<uint8_t *>(d_hard.p), d_phi_table.p, tab_last, N, log2G, done_flag());
   }
@@ -443,11 +455,11 @@ template <class Tr, class Idx> void select_for_precision(ldpc_b200_decoder *d) {
     case 4: d->k_cn = dev::cn_update_split_kernel<Tr, 4>; break;
     default: d->k_cn = dev::cn_update_split_kernel<Tr, 8>; break;
     }
-  } else if (d->cn_bulk) {
+  } else if (d->cn_bulk) { // plain passes staged by the bulk-copy engine; the fused-refill pass stays the register kernel
     switch (d->deg_cn) {
-    case 4: d->k_cn = dev::cn_update_bulk_kernel<Tr, 4>; break;
-    case 6: d->k_cn = dev::cn_update_bulk_kernel<Tr, 6>; break;
-    default: d->k_cn = dev::cn_update_bulk_kernel<Tr, 8>; break;
+    case 4: d->k_cn = dev::cn_update_bulk_kernel<Tr, 4>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 4, Idx>; break;
+    case 6: d->k_cn = dev::cn_update_bulk_kernel<Tr, 6>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 6, Idx>; break;
+    default: d->k_cn = dev::cn_update_bulk_kernel<Tr, 8>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 8, Idx>; break;
     }
   } else {
     switch (d->deg_cn) {
@@ -456,10 +468,18 @@ template <class Tr, class Idx> void select_for_precision(ldpc_b200_decoder *d) {
     default: d->k_cn = dev::cn_update_kernel<Tr, 8, Idx>; d->k_cn_refill = dev::cn_update_refill_kernel<Tr, 8, Idx>; break;
     }
   }
-  switch (d->deg_vn) {
-  case 4: d->k_vn = dev::vn_update_kernel<Tr, false, 4, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 4, Idx>; break;
-  case 6: d->k_vn = dev::vn_update_kernel<Tr, false, 6, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 6, Idx>; break;
-  default: d->k_vn = dev::vn_update_kernel<Tr, false, 8, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 8, Idx>; break;
+  if (d->vn_bulk) {
+    switch (d->deg_vn) {
+    case 4: d->k_vn = dev::vn_update_bulk_kernel<Tr, false, 4>; d->k_vnb = dev::vn_update_bulk_kernel<Tr, true, 4>; break;
+    case 6: d->k_vn = dev::vn_update_bulk_kernel<Tr, false, 6>; d->k_vnb = dev::vn_update_bulk_kernel<Tr, true, 6>; break;
+    default: d->k_vn = dev::vn_update_bulk_kernel<Tr, false, 8>; d->k_vnb = dev::vn_update_bulk_kernel<Tr, true, 8>; break;
+    }
+  } else {
+    switch (d->deg_vn) {
+    case 4: d->k_vn = dev::vn_update_kernel<Tr, false, 4, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 4, Idx>; break;
+    case 6: d->k_vn = dev::vn_update_kernel<Tr, false, 6, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 6, Idx>; break;
+    default: d->k_vn = dev::vn_update_kernel<Tr, false, 8, Idx>; d->k_vnb = dev::vn_update_kernel<Tr, true, 8, Idx>; break;
+    }
   }
 }
 
@@ -645,6 +665,7 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   if (const char *lw = std::getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(lw));
   d->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency() / local_world));
   if (const char *ht = std::getenv("LDPC_B200_HOST_THREADS")) d->host_threads = std::max(1, atoi(ht)); // feed experiments
+  if (const char *sl = std::getenv("LDPC_B200_STAGE_SLACK_PCT")) d->stage_slack_pct = uint32_t(std::min(100, std::max(0, atoi(sl))));
   d->precision = cfg->precision;
   d->elem = cfg->precision == LDPC_B200_FP32 ? 4 : 2;
   d->M = uint32_t(code.n_outputs());
@@ -774,6 +795,8 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   if (const char *e = std::getenv("LDPC_B200_CN_BULK"))
     d->cn_bulk = atoi(e) != 0 && d->cn_parts == 1 && code.max_degree_out() <= d->deg_cn &&
                  (1u << d->log2G) >= uint32_t(dev::kBulkTileVec);
+  if (const char *e = std::getenv("LDPC_B200_VN_BULK"))
+    d->vn_bulk = atoi(e) != 0 && code.max_degree_in() <= d->deg_vn && (1u << d->log2G) >= uint32_t(dev::kBulkTileVec);
   if (const char *e = std::getenv("LDPC_B200_DEG_VN")) d->deg_vn = atoi(e); // kernel experiments only
   if (const char *e = std::getenv("LDPC_B200_DEG_CN")) d->deg_cn = atoi(e);
   if (d->cn_parts > 1 && d->log2G < 5) { // a warp must stay inside one row: at least 32/G parts
@@ -806,8 +829,17 @@ ldpc_b200_status ldpc_b200_decoder_create(const ldpc_b200_code *code_h, const ld
   d->grid_cn = occupancy_grid(d->k_cn, d->threads_cn, d->smem_cn, d->n_sms, cn_items);
   if (d->k_cn_refill) d->grid_cn_refill = occupancy_grid(d->k_cn_refill, dev::kThreads, d->smem_tab, d->n_sms, cn_items);
   d->threads_vn = dev::vn_threads_for(d->deg_vn);
-  d->grid_vn = occupancy_grid(d->k_vn, d->threads_vn, d->smem_tab, d->n_sms, vn_items);
-  d->grid_vnb = occupancy_grid(d->k_vnb, d->threads_vn, d->smem_tab, d->n_sms, vn_items);
+  d->smem_vn = d->smem_tab;
+  if (d->vn_bulk) {
+    const int D = d->deg_vn == 4 ? 4 : (d->deg_vn == 6 ? 6 : 8), W = D <= 6 ? 8 : 12;
+    d->threads_vn = dev::kVnBulkThreads;
+    d->smem_vn = d->smem_tab + size_t(2) * dev::kVnBulkStages * (D + 1) * dev::kBulkTileVec * 16 +
+                 size_t(2) * dev::kVnBulkStages * W * 4 + size_t(2) * dev::kVnBulkStages * 8 + 64;
+    CU_TRY(cudaFuncSetAttribute(d->k_vn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_vn)));
+    CU_TRY(cudaFuncSetAttribute(d->k_vnb, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d->smem_vn)));
+  }
+  d->grid_vn = occupancy_grid(d->k_vn, d->threads_vn, d->smem_vn, d->n_sms, vn_items);
+  d->grid_vnb = occupancy_grid(d->k_vnb, d->threads_vn, d->smem_vn, d->n_sms, vn_items);
   d->grid_misc = d->n_sms * 8; // x 256 threads: a multiple of every row length G <= 2048 (refill_kernel keeps its g)
   CU_TRY(cudaStreamSynchronize(d->stream));
   *out = d.release();
@@ -834,8 +866,9 @@ uint32_t ldpc_b200_decoder_frames_in_flight(const ldpc_b200_decoder *dec) { retu
 ldpc_b200_status ldpc_b200_decoder_prepare_host_io(ldpc_b200_decoder *dec) {
   if (!dec) return fail(LDPC_B200_ERR_INVALID, "null decoder");
   CU_TRY(cudaSetDevice(dec->device));
-  ldpc_b200_status st = dec->ensure_input_staging();
-  if (st == LDPC_B200_OK) st = dec->ensure_syndrome_staging();
+  const uint32_t ring = dec->P + dec->stage_slack(dec->frames_in_flight, 32) + 32;
+  ldpc_b200_status st = dec->ensure_input_staging(ring);
+  if (st == LDPC_B200_OK) st = dec->ensure_syndrome_staging(ring);
   if (st == LDPC_B200_OK) st = dec->ensure_result_staging();
   return st;
 }
@@ -1054,7 +1087,7 @@ struct launch_timer {
 namespace {
 
 dev::SchedConst make_sched_const(const ldpc_b200_decoder *d, const ldpc_b200_decode_params *prm, uint32_t n_frames,
-                                 bool in_dev, bool syn_dev, bool res_dev) {
+                                 bool in_dev, bool syn_dev, bool res_dev, uint32_t slack_frames) {
   dev::SchedConst sc;
   memset(&sc, 0, sizeof(sc));
   const uint32_t B = std::min(n_frames, d->frames_in_flight); // num_vectors_gpu_batch
@@ -1075,14 +1108,16 @@ dev::SchedConst make_sched_const(const ldpc_b200_decoder *d, const ldpc_b200_dec
   sc.frame_stride = prm->frame_stride ? prm->frame_stride : sc.row_elems;
   sc.ring_block = frame_major ? 1u : 32u; // frames per interleaved staging block (64-128 B runs)
   // live staged frames are always inside [next_to_load, next_to_load + B) (+ block rounding)
-  sc.ring_frames = std::min<uint32_t>(d->P, ((B + sc.ring_block - 1) / sc.ring_block + 1) * sc.ring_block);
+  // (with no slack this is min(P, B rounded up to blocks + 1 block), as before)
+  sc.ring_frames = slack_frames ? ((B + slack_frames + sc.ring_block - 1) / sc.ring_block + 1) * sc.ring_block
+                                : std::min<uint32_t>(d->P, ((B + sc.ring_block - 1) / sc.ring_block + 1) * sc.ring_block);
   sc.input_mode = in_dev ? (frame_major ? 1u : 0u) : (frame_major ? 3u : 2u);
   sc.early_retire = (prm->flags & LDPC_B200_FLAG_EARLY_RETIRE) ? 1u : 0u;
   sc.log2_v = d->precision == LDPC_B200_FP32 ? 2u : 3u;
   // the flood kernels need at least 32 slots, and a warp of the split-row kernel must stay inside one row
   sc.min_log2_p_active = 5;
   if (d->cn_parts > 1) sc.min_log2_p_active = std::max<uint32_t>(5, ilog2(32u / uint32_t(d->cn_parts)) + sc.log2_v);
-  if (d->cn_bulk) sc.min_log2_p_active = ilog2(uint32_t(dev::kBulkTileVec)) + sc.log2_v; // whole tiles only
+  if (d->cn_bulk || d->vn_bulk) sc.min_log2_p_active = ilog2(uint32_t(dev::kBulkTileVec)) + sc.log2_v; // whole tiles only
   sc.syn_ring = syn_dev ? 0u : 1u;
   sc.results_ring = res_dev ? 0u : 1u;
   return sc;
@@ -1236,10 +1271,24 @@ private:
     const size_t row_dst_stride = size_t(ring_block) * es, row_src_stride = size_t(n_cols) * es;
     uint8_t *mirror = d->h_stage.p;
     const uint8_t *src = in_host;
+    // Rows of the caller's array are row_src_stride apart (8 KB for 4096 fp16 frames): every row is a new page and a
+    // new DRAM stream that the hardware prefetcher only picks up after a few lines, so the first lines of the rows a
+    // few iterations ahead are requested by hand.
+    const size_t first_src = chunks.empty() ? 0 : chunks.front().src;
+    const size_t run_bytes = chunks.empty() ? 0 : chunks.back().src + chunks.back().bytes - first_src;
+    constexpr size_t kAhead = 8;
     parallel_for(n_reg, d->host_threads, [&](size_t ia, size_t ib) {
       for (size_t i = ia; i < ib; ++i) {
         const uint8_t *row = src + i * row_src_stride;
         uint8_t *dst_row = mirror + i * row_dst_stride;
+#if defined(__SSE2__)
+        if (i + kAhead < ib) {
+          const char *pf = reinterpret_cast<const char *>(src + (i + kAhead) * row_src_stride + first_src);
+          _mm_prefetch(pf, _MM_HINT_T0);
+          if (run_bytes > 64) _mm_prefetch(pf + 64, _MM_HINT_T0);
+          if (run_bytes > 128) _mm_prefetch(pf + 128, _MM_HINT_T0);
+        }
+#endif
         for (const chunk_t &c : chunks) {
           // whole blocks (32 frames = 64 or 128 bytes) start on a 64-byte boundary of the mirror
           if (c.bytes == 64 && c.dst % 64 == 0) {
@@ -1358,7 +1407,11 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
   if (half_input && d->precision != LDPC_B200_FP32)
     return fail(LDPC_B200_ERR_INVALID, "HALF_INPUT is the transfer format of an FP32 decoder (an FP16 decoder takes halves anyway)");
   const int src_kind = packed ? dev::kSrcPackedBits : (half_input ? dev::kSrcHalf : dev::kSrcNative);
-  dev::SchedConst sc = make_sched_const(d, prm, n_frames, in_dev, syn_dev, res_dev);
+  // look-ahead slack of the staging ring (host-fed classic calls only: a decoder on a shared queue reserves, and so
+  // stages, only what the next check may load)
+  const bool frame_major_in = prm->input_layout != LDPC_B200_LAYOUT_INTERLEAVED;
+  const uint32_t slack = (in_dev || lq || n_frames <= B) ? 0u : d->stage_slack(B, frame_major_in ? 1u : 32u);
+  dev::SchedConst sc = make_sched_const(d, prm, n_frames, in_dev, syn_dev, res_dev, slack);
   sc.batch = B;
   sc.queue_block = lq ? lq->block : 0u;
   const dev::FrameQueueView qview = lq ? lq->view() : dev::FrameQueueView{nullptr, nullptr};
@@ -1369,11 +1422,11 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
   if (!in_dev && sc.ring_frames < std::min<uint32_t>(d->P, B + sc.ring_block) && sc.ring_frames < B)
     return fail(LDPC_B200_ERR_INVALID, "staging ring too small (internal error)");
   if (!in_dev) {
-    const ldpc_b200_status se = d->ensure_input_staging();
+    const ldpc_b200_status se = d->ensure_input_staging(sc.ring_frames);
     if (se != LDPC_B200_OK) return se;
   }
   if (!syn_dev) {
-    const ldpc_b200_status se = d->ensure_syndrome_staging();
+    const ldpc_b200_status se = d->ensure_syndrome_staging(sc.ring_frames);
     if (se != LDPC_B200_OK) return se;
   }
   if (!res_dev) {
@@ -1404,7 +1457,12 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
   feed.es_fm = packed ? 4 : (half_input ? 2 : d->elem);
   feed.frame_stride = sc.frame_stride;
   feed.lq = lq;
-  auto stage_upto = [&](uint32_t upto) { return feed.stage_upto(upto); };
+  auto stage_upto = [&](uint32_t upto) {
+    const double ts = now_s();
+    const ldpc_b200_status r = feed.stage_upto(upto);
+    rep.host_stage_s += now_s() - ts;
+    return r;
+  };
 
   // ---- optional per-launch timing (LDPC_B200_FLAG_TIME_KERNELS): see launch_timer
   launch_timer timer;
@@ -1430,6 +1488,7 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
   // ---- first batch: frames 0..B-1 into slots 0..B-1
   ldpc_b200_status st = stage_upto(B);
   if (st != LDPC_B200_OK) return st;
+  rep.first_batch_stage_s = rep.host_stage_s; // the device has nothing to do until the first batch is staged
   CU_TRY(cudaEventRecord(ev_first, d->stream));
   dev::sched_init_kernel<<<1, dev::kSchedThreads, 0, d->stream>>>(sc, d->d_state.p, d->d_in_gpu.p, d->d_virt.p,
                                                                   d_iter_start, d_iter_end, d->d_refill.p, d->d_n_new.p,
@@ -1563,8 +1622,14 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
     }
     // frames the next refill may need: at most B beyond what has been loaded so far
     if (lq) lq->reserve_upto(uint64_t(next_known) + queue_ahead);
-    st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, uint64_t(next_known) + B)));
-    if (st != LDPC_B200_OK) return st;
+    {
+      // the next check may load up to B frames beyond next_known: they must be staged before it runs.  With slack, a
+      // pass starts while a quarter of the slack is still staged beyond that, and fills the slack.
+      const uint64_t need = uint64_t(next_known) + B;
+      if (!slack || uint64_t(feed.staged) < std::min<uint64_t>(n_frames, need + slack / 4))
+        st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, need + slack)));
+      if (st != LDPC_B200_OK) return st;
+    }
     // service of this period + the next period's flood iterations (run ahead: no-ops once the scheduler has
     // set `done`).  The sequence is fixed, so it is captured once per parity into a CUDA graph and replayed.
     const int hg = int(period & 1);
@@ -1769,6 +1834,8 @@ ldpc_b200_status ldpc_b200_decode_multi(ldpc_b200_decoder *const *decs, uint32_t
     m.cn_refill_launches += r.cn_refill_launches;
     m.h2d_bytes += r.h2d_bytes, m.d2h_bytes += r.d2h_bytes;
     m.frames_refilled += r.frames_refilled, m.graph_launches += r.graph_launches, m.slot_iterations += r.slot_iterations;
+    m.host_stage_s = std::max(m.host_stage_s, r.host_stage_s);
+    m.first_batch_stage_s = std::max(m.first_batch_stage_s, r.first_batch_stage_s);
   }
   m.avg_iter = m.frames_decoded ? float(avg / double(m.frames_decoded)) : 0.f;
   // the reference's per-frame iteration time (ldpc_decoder_gpu.cu:627) over the frames in flight on all devices

@@ -36,7 +36,7 @@ namespace dev {
 #define LDPC_HMIN_CLAMP 1 // fp16 table index: packed-half clamp + byte offsets (A/B on B200: CN +2.4 %, VN +5.1 %)
 #endif
 #ifndef LDPC_REFILL_UNROLL
-#define LDPC_REFILL_UNROLL 4 // variables per loop trip of the priors-only refill kernel
+#define LDPC_REFILL_UNROLL 1 // variables per loop trip of the priors-only refill kernel (A/B: 1 -> 0.377 s, 4 -> 0.480 s, 8 -> 0.571 s per bench step)
 #endif
 #ifndef LDPC_MERGE_DECISION_STORES
 #define LDPC_MERGE_DECISION_STORES 1 // variable-node pass with decisions: one 32-bit store per 32 slots (see vn_update_kernel)
@@ -843,6 +843,123 @@ __global__ void __launch_bounds__(vn_threads_for(kMaxRegDeg), min_blocks_for(kMa
   }
 }
 
+// ---------------------------------------------------------------- variable-node pass, bulk-async (TMA) staged
+// Same arithmetic as vn_update_kernel, but a tile's rows (one variable x 256 frame vectors: the prior row and its
+// deg message rows, 4 KB each, wherever they lie) are gathered into shared memory by the bulk-copy engine
+// (cp.async.bulk + mbarrier complete_tx), updated in place by 256 threads and scattered back with cp.async.bulk
+// (bulk_group).  The copy engine moves a whole 4 KB row piece with one request instead of eight 512-byte warp loads,
+// and the threads never wait on global memory.
+// One CTA = 512 threads = TWO independent halves of 256 threads, each with its own 3-stage tile pipeline, mbarriers and
+// named barrier, sharing ONE copy of the phi table: (1 + D) x 4 KB x 3 stages x 2 halves + 39 KB table = 207 KB for
+// D = 6 -- two separate CTAs with a table each would only fit two stages, i.e. no load/compute overlap inside a CTA.
+// Needs every variable degree <= kMaxRegDeg and at least 256 vectors per row; selected by the host.
+constexpr int kVnBulkStages = 3;
+constexpr int kVnBulkThreads = 2 * kBulkTileVec;
+
+template <class Tr, bool kFinalBits, int kMaxRegDeg>
+__global__ void __launch_bounds__(kVnBulkThreads, 1)
+    vn_update_bulk_kernel(uint4 *__restrict__ msg, const uint4 *__restrict__ llr0, const uint32_t *__restrict__ vn_ell,
+                          const uint32_t *__restrict__, uint8_t *__restrict__ hard,
+                          const uint16_t *__restrict__ phi_table, uint32_t tab_last, uint32_t n_vars, uint32_t log2_g,
+                          const uint32_t *__restrict__ done) {
+  if (done && *done) return;
+  constexpr int kStages = kVnBulkStages;
+  constexpr int kRows = kMaxRegDeg + 1; // prior + messages
+  constexpr int kListWords = VnEll<kMaxRegDeg>::kWords;
+  extern __shared__ __align__(16) uint16_t s_table[]; // [table | 2 x stages | 2 x lists | 2 x barriers]
+  const uint32_t table_bytes = Tr::kUsesTable ? (tab_last / 8 + 1) * 16 : 0;
+  const uint32_t half = threadIdx.x / kBulkTileVec, tid = threadIdx.x % kBulkTileVec;
+  uint4 *stages_all = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(s_table) + table_bytes);
+  uint4 *stages = stages_all + size_t(half) * kStages * kRows * kBulkTileVec;
+  uint32_t *lists_all = reinterpret_cast<uint32_t *>(stages_all + size_t(2) * kStages * kRows * kBulkTileVec);
+  uint32_t *lists = lists_all + half * kStages * kListWords;
+  uint64_t *full = reinterpret_cast<uint64_t *>(lists_all + 2 * kStages * kListWords) + half * kStages;
+  const uint16_t *tab = stage_phi_table<Tr>(phi_table, tab_last); // all 512 threads; ends with __syncthreads if staged
+  const uint32_t G = 1u << log2_g;
+  const uint32_t GA = 1u << active_log2(done, log2_g);
+  const size_t hard_row_bytes = (size_t(G) * Tr::kFramesPerVec) >> 3;
+  const uint32_t tiles_per_row = GA / kBulkTileVec;
+  const uint64_t total = uint64_t(n_vars) * tiles_per_row;
+  if (tid == 0)
+    for (int sidx = 0; sidx < kStages; ++sidx) bulk::mbar_init(full + sidx, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  auto half_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1u + half), "n"(kBulkTileVec) : "memory"); };
+  const uint64_t lane_tile = uint64_t(blockIdx.x) * 2 + half, tile_stride = uint64_t(gridDim.x) * 2;
+  auto tile_of = [&](uint64_t i) { return lane_tile + i * tile_stride; };
+  auto issue = [&](uint64_t i) { // elected thread: gather tile i's rows into stage i % kStages
+    const uint64_t t = tile_of(i);
+    if (t >= total) return;
+    const uint32_t v = uint32_t(t / tiles_per_row), gb = uint32_t(t - uint64_t(v) * tiles_per_row);
+    const int sidx = int(i % kStages);
+    uint32_t *list = lists + sidx * kListWords;
+    const uint4 *e = reinterpret_cast<const uint4 *>(vn_ell) + size_t(v) * (kListWords / 4);
+#pragma unroll
+    for (int q = 0; q < kListWords / 4; ++q) reinterpret_cast<uint4 *>(list)[q] = __ldg(e + q);
+    const uint32_t deg = list[0];
+    uint4 *tile = stages + size_t(sidx) * kRows * kBulkTileVec;
+    bulk::mbar_expect_tx(full + sidx, (deg + 1) * kBulkTileVec * 16u); // release: the list is visible to the waiters
+    bulk::load_bulk(tile, llr0 + (size_t(v) << log2_g) + size_t(gb) * kBulkTileVec, kBulkTileVec * 16u, full + sidx);
+    for (uint32_t k = 0; k < deg; ++k)
+      bulk::load_bulk(tile + size_t(1 + k) * kBulkTileVec, msg + (size_t(list[1 + k]) << log2_g) + size_t(gb) * kBulkTileVec,
+                      kBulkTileVec * 16u, full + sidx);
+  };
+  if (tid == 0)
+    for (int i = 0; i < kStages - 1; ++i) issue(uint64_t(i));
+  for (uint64_t i = 0; tile_of(i) < total; ++i) {
+    const uint64_t t = tile_of(i);
+    const uint32_t v = uint32_t(t / tiles_per_row), gb = uint32_t(t - uint64_t(v) * tiles_per_row);
+    const uint32_t g = gb * kBulkTileVec + tid;
+    const int sidx = int(i % kStages);
+    uint4 *tile = stages + size_t(sidx) * kRows * kBulkTileVec;
+    const uint32_t *list = lists + sidx * kListWords;
+    bulk::mbar_wait(full + sidx, uint32_t((i / kStages) & 1));
+    const uint32_t deg = list[0];
+    uint4 T = tile[tid];
+    uint4 m[kMaxRegDeg];
+#pragma unroll
+    for (int k = 0; k < kMaxRegDeg; ++k)
+      if (k < int(deg)) m[k] = tile[size_t(1 + k) * kBulkTileVec + tid];
+#pragma unroll
+    for (int k = 0; k < kMaxRegDeg; ++k)
+      if (k < int(deg)) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) word(T, w) = Tr::add_w(word(T, w), word(m[k], w));
+      }
+#pragma unroll
+    for (int k = 0; k < kMaxRegDeg; ++k)
+      if (k < int(deg)) tile[size_t(1 + k) * kBulkTileVec + tid] = vn_out_vec<Tr>(T, m[k], tab, tab_last);
+    if (kFinalBits) {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) bits |= Tr::hard_bits(word(T, w)) << (w * Tr::kFramesPerWord);
+      uint8_t *row = hard + size_t(v) * hard_row_bytes;
+      if (Tr::kFramesPerVec == 8) {
+        uint32_t b = bits | (__shfl_down_sync(0xFFFFFFFFu, bits, 1) << 8);
+        b |= __shfl_down_sync(0xFFFFFFFFu, b, 2) << 16;
+        if ((g & 3u) == 0) *reinterpret_cast<uint32_t *>(row + g) = b;
+      } else {
+        uint32_t b = bits | (__shfl_down_sync(0xFFFFFFFFu, bits, 1) << 4);
+        b |= __shfl_down_sync(0xFFFFFFFFu, b, 2) << 8;
+        b |= __shfl_down_sync(0xFFFFFFFFu, b, 4) << 16;
+        if ((g & 7u) == 0) *reinterpret_cast<uint32_t *>(row + (g >> 1)) = b;
+      }
+    }
+    bulk::fence_async_smem(); // generic-proxy writes -> visible to the bulk-copy (async) proxy
+    half_sync();
+    if (tid == 0) {
+      for (uint32_t k = 0; k < deg; ++k)
+        bulk::store_bulk(msg + (size_t(list[1 + k]) << log2_g) + size_t(gb) * kBulkTileVec,
+                         tile + size_t(1 + k) * kBulkTileVec, kBulkTileVec * 16u);
+      bulk::store_commit();
+      // the stage tile i-1 used (and its list) may be refilled once its write-back has finished READING shared memory
+      bulk::store_wait_read<1>();
+      issue(i + kStages - 1);
+    }
+  }
+  if (tid == 0) bulk::store_wait_all();
+}
+
 // ---------------------------------------------------------------- syndrome check (bit-sliced)
 // One thread = (check c, 32-slot word w): x = syn[c][w] xor hard[var(e)][w] over the row; any set bit marks
 // that slot's frame as violated (flood.cu:191-223, 32 frames per XOR).
@@ -928,8 +1045,9 @@ __global__ void __launch_bounds__(kThreads)
   }
 #pragma unroll
   for (int w = 0; w < 4; ++w) word(SEL, w) = Tr::lane_mask(nm >> (w * Tr::kFramesPerWord));
-  // kUnroll variables per trip (priors-only variant): the loads of a trip are independent, a thread's trips are not, and
-  // with only ~1800 trips per thread the launch was latency-bound at one variable per trip
+  // kUnroll variables per trip (priors-only variant).  More than one per trip turned out SLOWER (profiles/
+  // r06_ab_fused_refill.txt): the launch is bound by the sector traffic of its scattered source reads, and a wider
+  // window of variables in flight only evicts the sectors neighbouring threads are about to use.
   constexpr int kUnroll = kMsgRows ? 1 : LDPC_REFILL_UNROLL;
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t item = first; item < total; item += kUnroll * stride) {

@@ -20,7 +20,7 @@ def build(specs):
     for spec in specs:
         name, _, flags = spec.partition("=")
         out = os.path.join(AB, f"lib_{name}.so")
-        cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+        cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++14", "-lineinfo",
                "-Xcompiler", "-fPIC", "-shared", "-o", out, "ldpc_b200.cu", "ldpc_code.cpp"] + [f for f in flags.split(",") if f]
         procs.append((name, subprocess.Popen(cmd, cwd=CSRC)))
     for name, p in procs:

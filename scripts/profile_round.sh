@@ -4,7 +4,7 @@
 # Outputs go to gpurun_out/; summarise them into profiles/ with scripts/summarise_profile.py.
 set -u
 TAG=${1:-rXX}
-CMD="python bench.py --loading 2 --steps 1 --warmup 1 --skip-cpu --skip-e2e"
+CMD="python bench.py --loading 2 --steps 1 --warmup 1 --skip-cpu --skip-e2e --skip-extra"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
 tail -1 gpurun_out/${TAG}_plain.log | cut -c1-200
