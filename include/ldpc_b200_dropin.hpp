@@ -98,6 +98,11 @@ public:
 
   // ldpc_decoder_gpu.cu:20-157: validate the graph, size the frames in flight from device memory, allocate, upload
   decoder(const code_t &p_code, const channel_t &p_channel, const static_params_t &p_params) : m_channel(p_channel) {
+    // a caller compiled against another version of ldpc_b200.h than the library would corrupt its own stack
+    uint32_t abi[4] = {0, 0, 0, 0};
+    ldpc_b200_abi_sizes(abi);
+    if (abi[1] != sizeof(ldpc_b200_config) || abi[2] != sizeof(ldpc_b200_decode_params) || abi[3] != sizeof(ldpc_b200_report))
+      throw error_t(std::string("ldpc_b200.h and libldpc_b200.so disagree on the struct layouts: rebuild the caller"));
     const uint32_t M = uint32_t(p_code.n_outputs()), N = uint32_t(p_code.n_inputs()), E = p_code.n_edges();
     std::vector<uint32_t> row_ptr(size_t(M) + 1), col_idx(E);
     for (uint32_t c = 0; c < M; ++c) row_ptr[c] = p_code.out_bit_to_edge(c);

@@ -288,11 +288,13 @@ struct ldpc_b200_decoder {
     if (!h_stage_syn.p || h_stage_syn.n < need) CU_TRY(h_stage_syn.alloc(need));
     return LDPC_B200_OK;
   }
-  // Host-fed calls stage frames in passes of several hundred frames instead of one pass per check period: the ring
-  // holds frames_in_flight + slack frames; a pass is started when fewer than a quarter of the slack is staged beyond
-  // what the next check may need, and fills the slack.  Each pass then reads kilobyte runs of every row of the caller's
-  // strided array instead of the ~900 bytes a single period consumes (fewer page walks and DRAM streams per frame).
-  uint32_t stage_slack_pct = 50; // LDPC_B200_STAGE_SLACK_PCT
+  // EXPERIMENT, off by default (LDPC_B200_STAGE_SLACK_PCT > 0): stage host frames in passes of a few thousand frames
+  // instead of one pass per check period -- the ring then holds frames_in_flight + slack frames, a pass starts when
+  // fewer than a quarter of the slack is staged beyond what the next check may need, and fills the slack, so it reads
+  // kilobyte runs of every row of the caller's strided array instead of the ~900 bytes one period consumes.  Measured
+  // (scripts/e2e_feed.sh, 4096 distinct frames, 4 host threads): 15.06 s per e2e step with 50 % slack against 14.89 s
+  // without (2 threads: 16.04 vs 15.34 s): the big passes are bursts the flood iterations of ONE period cannot hide.
+  uint32_t stage_slack_pct = 0;
   uint32_t stage_slack(uint32_t batch, uint32_t ring_block) const {
     return uint32_t(uint64_t(batch) * stage_slack_pct / 100) / ring_block * ring_block;
   }
