@@ -209,6 +209,9 @@ ldpc_b200_status ldpc_b200_queue_create(const char *shm_name, int32_t create, ui
 void ldpc_b200_queue_destroy(ldpc_b200_queue *queue);
 uint32_t ldpc_b200_queue_size(const ldpc_b200_queue *queue);
 void ldpc_b200_queue_reset(ldpc_b200_queue *queue); /* cursor back to frame 0 (no decoder may be drawing from it) */
+/* Reserve the next block by hand (what a decoder does internally; for callers that schedule frames themselves and for
+ * tests): returns the number of frames reserved (0: queue exhausted) and their first frame index. */
+uint32_t ldpc_b200_queue_take(ldpc_b200_queue *queue, uint32_t *first_frame);
 /* Like ldpc_b200_decode, with input / syndromes / results / iter_counts sized for the WHOLE queue (or a pool, see
  * input_pool_frames); only the rows of the frames this decoder took are read and written; report->frames_decoded
  * says how many those were.  Call it concurrently, once per decoder. */

@@ -269,6 +269,12 @@ class FrameQueue:
     def reset(self):
         _lib.lib().ldpc_b200_queue_reset(self._h)
 
+    def take(self):
+        """Reserve the next block by hand: (first_frame, count), count == 0 when the queue is exhausted."""
+        first = C.c_uint32(0)
+        n = _lib.lib().ldpc_b200_queue_take(self._h, C.byref(first))
+        return int(first.value), int(n)
+
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.lib().ldpc_b200_queue_destroy(self._h)

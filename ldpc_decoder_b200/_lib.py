@@ -73,6 +73,7 @@ SYMBOLS = {
     "ldpc_b200_queue_destroy": (None, [C.c_void_p]),
     "ldpc_b200_queue_size": (C.c_uint32, [C.c_void_p]),
     "ldpc_b200_queue_reset": (None, [C.c_void_p]),
+    "ldpc_b200_queue_take": (C.c_uint32, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "ldpc_b200_decode_from_queue": (C.c_int, [C.c_void_p, C.POINTER(DecodeParams), C.c_void_p, _VP, _VP, _VP,
                                               C.POINTER(Report), _VP]),
     "ldpc_b200_decode_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(DecodeParams), C.c_uint32, _VP, _VP,

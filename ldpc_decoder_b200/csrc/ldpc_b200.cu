@@ -1772,6 +1772,14 @@ void ldpc_b200_queue_destroy(ldpc_b200_queue *q) { delete q; }
 
 uint32_t ldpc_b200_queue_size(const ldpc_b200_queue *q) { return q ? q->sh->n_total : 0; }
 
+uint32_t ldpc_b200_queue_take(ldpc_b200_queue *q, uint32_t *first_frame) {
+  if (!q || !first_frame) return 0;
+  const uint64_t start = q->sh->cursor.fetch_add(q->sh->block, std::memory_order_relaxed);
+  if (start >= q->sh->n_total) return 0;
+  *first_frame = uint32_t(start);
+  return uint32_t(std::min<uint64_t>(q->sh->block, q->sh->n_total - start));
+}
+
 void ldpc_b200_queue_reset(ldpc_b200_queue *q) {
   if (q) q->sh->cursor.store(0);
 }

@@ -77,3 +77,71 @@ def test_two_rank_gloo_sharded_decode(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+QUEUE_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch
+import torch.distributed as dist
+import ldpc_decoder_b200 as L
+from ldpc_decoder_b200 import alist, harness
+from oracle import binding as ob
+
+rank = int(sys.argv[1])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+# one queue of frames in POSIX shared memory, two processes (what bench.py --gpus N does with one process per GPU):
+# rank 0 creates it, rank 1 opens it; every process takes blocks until the cursor has passed the end
+name = "ldpc_b200_gloo_test_{port}"
+n_total, block = 53, 4
+q = L.FrameQueue(n_total, block, shm_name=name, create=True) if rank == 0 else None
+dist.barrier()
+if rank != 0:
+    q = L.FrameQueue(shm_name=name, create=False)
+assert q.size == n_total
+gen = alist.make_regular_code(384, 3, 6, seed=21)
+inp, syn, bits = harness.make_frames(gen, n_total, "awgn", 0.74, seed=5)
+prm = harness.channel_param("awgn", 0.74)
+code = ob.OracleCode(text=alist.alist_text(gen))
+res = np.zeros((n_total, gen.n_vars // 32), dtype=np.uint32)
+mine = np.zeros(n_total, dtype=np.int64)
+while True:
+    first, cnt = q.take()
+    if cnt == 0:
+        break
+    assert first % block == 0 and cnt == min(block, n_total - first)
+    # the CPU oracle stands in for the per-GPU decoder (test infrastructure): decode this block's frames
+    r, it, _ = ob.OracleDecoder(code, ob.FP32, 2, n_threads=1).decode(ob.AWGN, prm, 40, 5, inp[:, first:first + cnt].copy(),
+                                                                       syn[first:first + cnt].copy())
+    res[first:first + cnt] = r
+    mine[first:first + cnt] = 1
+taken = torch.from_numpy(mine.copy())
+dist.all_reduce(taken)
+assert taken.min().item() == 1 and taken.max().item() == 1, "every frame decoded by exactly one process"
+merged = torch.from_numpy(res.astype(np.int64))
+dist.all_reduce(merged)  # disjoint rows: the sum is the union (the host-side merge; no collective on the data path)
+assert harness.count_bit_errors(merged.numpy().astype(np.uint32), bits).sum() == 0
+dist.barrier()
+q.close()
+dist.destroy_process_group()
+print("rank", rank, "ok", int(mine.sum()))
+"""
+
+
+def test_two_processes_share_one_frame_queue(tmp_path):
+    """The shared frame queue across PROCESSES (one per GPU on a GPU box): POSIX shared-memory cursor, rank 0 creates,
+    rank 1 opens, blocks are disjoint and cover the queue; world_size-2 gloo, the CPU oracle as the per-rank decoder."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "queue_worker.py"
+    script.write_text(QUEUE_WORKER.format(root=ROOT, port=port))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True, env=env) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
