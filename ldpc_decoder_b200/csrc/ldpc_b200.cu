@@ -349,8 +349,14 @@ struct ldpc_b200_decoder {
                                                                         d_viol.p, M, log2PW, done_flag());
   }
   // refill kernels: entries, count, masks are already in device memory (scheduler kernel or host upload)
+  // staged_src: the source is interleaved (element [i][frame], or the staging ring's blocks of 32 frames)
+  // LDPC_B200_REFILL_STAGED=1: stage the channel values of interleaved sources through shared memory (coalesced source
+  // reads).  Measured in bench steps (profiles/r06_ab_fused_refill.txt): 0.394 s of refill per step against 0.383 s with
+  // per-lane loads -- the refill is bound by the scattered 16-byte read-modify-writes, not by its source reads.  Off.
+  bool refill_staged = false;
   void launch_refill_kernels(const void *src, const uint32_t *src_syn, int channel, float param, int src_kind = 0,
-                             bool msg_rows = true, uint32_t gate = dev::kGateNone, bool with_syndromes = true) {
+                             bool msg_rows = true, uint32_t gate = dev::kGateNone, bool with_syndromes = true,
+                             bool staged_src = false) {
     const uint32_t n_regular = N - n_erased;
     uint4 *msg = reinterpret_cast<uint4 *>(d_msg.p), *l0 = reinterpret_cast<uint4 *>(d_llr0.p);
     auto launch = [&](auto kernel, const uint16_t *table) {
@@ -358,6 +364,22 @@ struct ldpc_b200_decoder {
                                                       d_col_ptr.p, d_in_to_out.p, table, N, n_regular, log2G, channel,
                                                       param, done_flag(), gate, d_var_pos.p);
     };
+    // priors-only refill of an interleaved source: channel values staged through shared memory (coalesced source reads)
+    if (!msg_rows && staged_src && src_kind != dev::kSrcPackedBits && refill_staged && (1u << log2G) >= uint32_t(dev::kThreads)) {
+      const size_t es = (precision == LDPC_B200_FP16 || src_kind == dev::kSrcHalf) ? 2 : 4;
+      uint32_t rows = 4;
+      while (rows > 1 && size_t(rows) * P * es > 64 * 1024) rows >>= 1;
+      const size_t smem = size_t(rows) * P * es;
+      auto launch_staged = [&](auto kernel) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        kernel<<<grid_misc, dev::kThreads, smem, stream>>>(l0, src, d_refill.p, d_n_new.p, d_new_mask.p, d_slot_entry.p, N,
+                                                           n_regular, log2G, channel, param, done_flag(), gate,
+                                                           d_var_pos.p, rows);
+      };
+      if (precision == LDPC_B200_FP16) launch_staged(dev::refill_priors_staged_kernel<dev::TraitsF16, dev::kSrcNative>);
+      else if (src_kind == dev::kSrcHalf) launch_staged(dev::refill_priors_staged_kernel<dev::TraitsF32, dev::kSrcHalf>);
+      else launch_staged(dev::refill_priors_staged_kernel<dev::TraitsF32, dev::kSrcNative>);
+    } else
     // src_kind: dev::kSrcNative / kSrcPackedBits / kSrcHalf (half elements into an fp32 decoder)
     if (precision == LDPC_B200_FP32) {
       if (src_kind == dev::kSrcPackedBits)
@@ -512,6 +534,7 @@ ldpc_b200_status select_kernels(ldpc_b200_decoder *d) {
   d->fused_mode = -1;
   if (const char *fused = std::getenv("LDPC_B200_FUSED_REFILL")) d->fused_mode = atoi(fused) != 0 ? 1 : 0;
   if (const char *pct = std::getenv("LDPC_B200_FUSED_MIN_PCT")) d->fused_min_pct = uint32_t(std::max(0, atoi(pct)));
+  if (const char *e = std::getenv("LDPC_B200_REFILL_STAGED")) d->refill_staged = atoi(e) != 0;
   if (d->fused_mode == 0) d->k_cn_refill = nullptr;
   return LDPC_B200_OK;
 }
@@ -1498,7 +1521,8 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
                                                                   qview);
   auto enqueue_refill = [&]() {
     if (fused_any) {
-      d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, false, dev::kGateFused, true);
+      d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, false, dev::kGateFused, true,
+                               !frame_major);
       d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, true, dev::kGatePlain, false);
     } else {
       d->launch_refill_kernels(src_dev, syn_src_dev, prm->channel, prm->channel_param, src_kind, true);

@@ -1124,6 +1124,84 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Priors-only refill with the new frames' channel values STAGED THROUGH SHARED MEMORY (interleaved sources, rows of
+// at least 256 vectors).  In refill_kernel every new lane reads its 2- or 4-byte channel value with a load of its own:
+// one 32-byte sector request per (new lane, variable) -- 8-12 ms per refilling period at 2^12 slots, more than the
+// read-modify-write of the prior vectors itself.  The frames a check loads are CONSECUTIVE frames, i.e. consecutive
+// columns of a variable's row in the caller's array (or runs of 32 in the staging ring), so here a CTA first copies
+// the values of rows_per_trip variables for ALL new frames into shared memory with coalesced loads (entry t = t-th
+// new frame), then every thread picks the values of its new lanes by entry index.  One CTA = 256 consecutive vectors
+// of a row; the CTAs of a row walk the variables together.
+template <class Tr, int kSrc>
+__global__ void __launch_bounds__(kThreads)
+    refill_priors_staged_kernel(uint4 *__restrict__ llr0, const void *__restrict__ src,
+                                const RefillEntry *__restrict__ entries, const uint32_t *__restrict__ n_new_ptr,
+                                const uint32_t *__restrict__ new_mask, const uint32_t *__restrict__ slot_entry,
+                                uint32_t n_vars, uint32_t n_regular, uint32_t log2_g, int channel, float param,
+                                const uint32_t *__restrict__ ctl, uint32_t gate, const uint32_t *__restrict__ var_pos,
+                                uint32_t rows_per_trip) {
+  const uint32_t n_new = *n_new_ptr;
+  if (n_new == 0) return;
+  if (gated_off(ctl, gate)) return;
+  constexpr int V = Tr::kFramesPerVec;
+  constexpr uint32_t kFull = (1u << V) - 1u;
+  constexpr bool kHalfElems = V == 8 || kSrc == kSrcHalf;
+  typedef typename std::conditional<kHalfElems, uint16_t, uint32_t>::type src_t;
+  extern __shared__ __align__(16) uint8_t s_stage_raw[];
+  src_t *s_val = reinterpret_cast<src_t *>(s_stage_raw); // [rows_per_trip][n_new]
+  const uint32_t ctas_per_row = (1u << log2_g) / kThreads;  // >= 1 (host)
+  const uint32_t g = (blockIdx.x % ctas_per_row) * kThreads + threadIdx.x;
+  const uint32_t group = blockIdx.x / ctas_per_row, n_groups = gridDim.x / ctas_per_row;
+  const uint32_t nm = load_frame_bits<Tr>(reinterpret_cast<const uint8_t *>(new_mask), g);
+  uint32_t ent[V];
+  uint4 SEL;
+#pragma unroll
+  for (int j = 0; j < V; ++j) ent[j] = ((nm >> j) & 1u) ? __ldg(slot_entry + g * V + j) : 0u;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) word(SEL, w) = Tr::lane_mask(nm >> (w * Tr::kFramesPerWord));
+  const uint64_t src_stride = entries[0].src_stride; // the same for every frame of a launch
+  const src_t *sp = static_cast<const src_t *>(src);
+  for (uint32_t i0 = group * rows_per_trip; i0 < n_vars; i0 += n_groups * rows_per_trip) {
+    for (uint32_t t = threadIdx.x; t < n_new; t += kThreads) {
+      const uint64_t off = entries[t].src_offset;
+      for (uint32_t r = 0; r < rows_per_trip; ++r) {
+        const uint32_t i = i0 + r;
+        if (i < n_regular) s_val[r * n_new + t] = __ldg(sp + off + uint64_t(i) * src_stride);
+      }
+    }
+    __syncthreads();
+    if (nm) {
+      for (uint32_t r = 0; r < rows_per_trip; ++r) {
+        const uint32_t i = i0 + r;
+        if (i >= n_vars) break;
+        uint4 L = make_uint4(0, 0, 0, 0);
+        if (i < n_regular) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            if ((nm >> j) & 1u) {
+              const src_t raw = s_val[r * n_new + ent[j]];
+              if (V == 4) {
+                const uint32_t wide = kSrc == kSrcHalf ? __float_as_uint(__half2float(__ushort_as_half(uint16_t(raw)))) : uint32_t(raw);
+                word(L, j & 3) = TraitsF32::to_llr(wide, channel, param);
+              } else {
+                word(L, (j >> 1) & 3) |= uint32_t(TraitsF16::to_llr(uint16_t(raw), channel, param)) << ((j & 1) * 16);
+              }
+            }
+          }
+        }
+        const uint32_t vrow = var_pos ? __ldg(var_pos + i) : i;
+        uint4 *p = llr0 + (size_t(vrow) << log2_g) + g;
+        uint4 old = make_uint4(0, 0, 0, 0);
+        if (nm != kFull) old = ld_stream(p);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) word(old, w) = (word(old, w) & ~word(SEL, w)) | word(L, w);
+        st_stream(p, old);
+      }
+    }
+    __syncthreads(); // the staged values are overwritten by the next trip
+  }
+}
+
 // Target syndromes of the new frames: frame-major packed words (bit c%32 of word c/32) -> bit-sliced syn[c][slot word].
 // One thread = (group of 32 checks, slot word w) for words that received new frames: it loads ONE source word per new
 // slot of its word (the 32 target bits of that frame for its checks) and then rewrites its 32 syn words, inserting bit

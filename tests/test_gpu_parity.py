@@ -940,6 +940,53 @@ def test_fused_refill_equals_stand_alone_refill(small_codes, prec, name, channel
     assert np.array_equal(it, ia) and rept["cn_refill_s"] > 0 and rept["cn_refill_launches"] == repa["cn_refill_launches"]
 
 
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_staged_refill_equals_per_lane_refill(prec, monkeypatch):
+    """LDPC_B200_REFILL_STAGED=1 (measured, not the default): the priors-only refill stages the new frames' channel
+    values through shared memory (coalesced source reads, refill_priors_staged_kernel) when a row holds at least 256
+    vectors and the source is interleaved; the default keeps the per-lane loads of refill_kernel.  Identical results and message state, for
+    device-resident inputs (element [i][frame]), host inputs (staging ring of 32-frame blocks) and half transfer."""
+    import torch
+
+    from ldpc_decoder_b200 import alist
+
+    gen = alist.make_readme_shaped_code(13, seed=5)
+    code = L.Code.from_generated(gen)
+    fp16 = prec == "fp16"
+    log2p = 11 if fp16 else 10
+    P = 1 << log2p
+    n = 3 * P + 77
+    inp, syn, bits, prm = _frames(gen, 300, "awgn", 0.6, 13, np.float16 if fp16 else np.float32)
+    monkeypatch.setenv("LDPC_B200_FUSED_REFILL", "1")
+    monkeypatch.setenv("LDPC_B200_REFILL_STAGED", "1")
+    a = L.Decoder(code, L.FP16 if fp16 else L.FP32, log2p)
+    monkeypatch.setenv("LDPC_B200_REFILL_STAGED", "0")
+    b = L.Decoder(code, L.FP16 if fp16 else L.FP32, log2p)
+    kw = dict(n_frames=n, num_iter_max=40, pool_frames=300)
+    ra, ia, repa = a.decode(L.AWGN, prm, inp, syn, **kw)           # host-fed: ring of 32-frame blocks
+    rb_, ib, _ = b.decode(L.AWGN, prm, inp, syn, **kw)
+    assert repa["cn_refill_launches"] > 0
+    assert np.array_equal(ia, ib) and np.array_equal(ra, rb_)
+    for s in (0, 1, 255, P - 1):
+        assert np.array_equal(a.messages(s).view(np.uint32), b.messages(s).view(np.uint32)), s
+        assert np.array_equal(a.priors(s).view(np.uint32), b.priors(s).view(np.uint32)), s
+    d_in = torch.from_numpy(inp.view(np.int16) if fp16 else inp).cuda()
+    d_syn = torch.from_numpy(syn.view(np.int32)).cuda()
+    res = []
+    for d in (a, b):
+        d_res = torch.zeros((n, gen.n_vars // 32), dtype=torch.int32, device="cuda")
+        _, it, _ = d.decode(L.AWGN, prm, d_in, d_syn, results=d_res, **kw)   # device-resident: element [i][frame]
+        res.append((d_res.cpu().numpy().view(np.uint32), it))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][0], ra) and np.array_equal(res[0][1], ia)
+    if not fp16:
+        half = inp.astype(np.float16)
+        rh_a, ih_a, _ = a.decode(L.AWGN, prm, half, syn, flags=L.FLAG_HALF_INPUT, **kw)
+        rh_b, ih_b, _ = b.decode(L.AWGN, prm, half, syn, flags=L.FLAG_HALF_INPUT, **kw)
+        assert np.array_equal(rh_a, rh_b) and np.array_equal(ih_a, ih_b)
+    assert harness.count_bit_errors(ra, np.tile(bits, (n // 300 + 1, 1))[:n])[ia < 40].sum() == 0
+
+
 def test_fused_refill_long_rows(monkeypatch):
     """Fused refill on check rows longer than the register-resident degree (the two-pass path of the check-node pass)."""
     from ldpc_decoder_b200 import alist
