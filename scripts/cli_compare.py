@@ -34,15 +34,30 @@ def run(log2n, sigma, prec, extra=("-p", "8", "-m", "2", "-e", "15", "-i", "120"
     return summary(ref), summary(new), ref, new
 
 
+def run_dropin(path, sigma, prec, extra=("-p", "8", "-m", "2", "-e", "15", "-i", "120")):
+    """The reference's OWN main.cpp compiled unchanged against include/ldpc_decoder_gpu.h and linked with
+    libldpc_b200.so (oracle/Makefile refdropin)."""
+    args = ["-f", path, "-c", "1", "-n", str(sigma)] + list(extra)
+    exe = os.path.join(ROOT, "oracle", "_ref", f"dropin_ldpc_decoder_{prec}")
+    out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=900).stdout
+    return summary(out), out
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     res = {}
+    gen = alist.make_readme_shaped_code(20, seed=1)
+    path = os.path.join(tempfile.mkdtemp(), "standin_20.alist")
+    alist.write_alist(gen, path)
     for prec in ("fp16", "fp32"):
-        r, n, rt, nt = run(20, 0.82, prec)
-        res[prec] = {"reference_cli": r, "b200_cli": n}
+        r, n, rt, nt = run(20, 0.82, prec, path=path)
+        dsum, dt = run_dropin(path, 0.82, prec)
+        res[prec] = {"reference_cli": r, "b200_cli": n, "reference_main_cpp_on_dropin_header": dsum}
+        print(prec, "dropin   :", {k: v for k, v in dsum.items() if k != "description"})
+        open(os.path.join(ROOT, "gpurun_out", f"r06_cli_{prec}_reference_main_on_dropin.txt"), "w").write(dt)
         print(prec, "reference:", {k: v for k, v in r.items() if k != "description"})
         print(prec, "b200     :", {k: v for k, v in n.items() if k != "description"})
         print(prec, "description identical:", r["description"] == n["description"])
-        open(os.path.join(ROOT, "gpurun_out", f"r01_cli_{prec}_reference.txt"), "w").write(rt)
-        open(os.path.join(ROOT, "gpurun_out", f"r01_cli_{prec}_b200.txt"), "w").write(nt)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r01_cli_compare.json"), "w"), indent=1)
+        open(os.path.join(ROOT, "gpurun_out", f"r06_cli_{prec}_reference.txt"), "w").write(rt)
+        open(os.path.join(ROOT, "gpurun_out", f"r06_cli_{prec}_b200.txt"), "w").write(nt)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r06_cli_compare.json"), "w"), indent=1)

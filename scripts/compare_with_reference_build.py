@@ -32,4 +32,4 @@ for prec, log2p, load in (("fp16", 8, 2), ("fp32", 8, 2), ("fp16", 10, 2), ("fp3
            "speedup": t_ref / t_new, "decisions_identical": same, "ref_avg_iter": rrep["avg_iter"]}
     out.append(row); print(json.dumps(row), flush=True)
     del dec
-json.dump(out, open("gpurun_out/r01_vs_reference_build.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/r06_vs_reference_build.json", "w"), indent=1)

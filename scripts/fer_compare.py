@@ -55,4 +55,4 @@ if __name__ == "__main__":
     allr = {}
     for sigma in (0.805, 0.82, 0.83, 0.84):
         allr[str(sigma)] = run(n_frames=2048, sigma=sigma)
-    json.dump(allr, open("gpurun_out/r01_fer_compare.json", "w"), indent=1)
+    json.dump(allr, open("gpurun_out/r06_fer_compare.json", "w"), indent=1)
