@@ -46,7 +46,13 @@ def parse_args():
     ap.add_argument("--pool", type=int, default=4096,
                     help="distinct synthetic frames (recycled): 4096 fp16 frames = 8.6 GB, so the strided gather of the "
                          "host-fed leg walks an 8 KB row stride as it would with all-distinct frames")
-    ap.add_argument("--small-pool", type=int, default=128, help="pool of the secondary e2e figure (round-1 bench: 128)")
+    ap.add_argument("--small-pool", type=int, default=0,
+                    help="also time the e2e leg on a pool of this many frames (round-1 bench: 128; 256-byte rows)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the e2e leg (at most --steps)")
+    ap.add_argument("--time-budget", type=float, default=760.0,
+                    help="seconds this process may take in total (the driver's scaling run allows 870 s per N): legs "
+                         "beside the headline and the e2e figure are skipped, and named in `skipped_legs`, when the "
+                         "time left does not cover their estimated cost")
     ap.add_argument("--skip-extra", action="store_true",
                     help="skip the legs beside the headline: reference CUDA build, other BASELINE configs, shared queue")
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames of the bounded CPU sample")
@@ -381,10 +387,25 @@ def ref_cuda_build_leg(L, gen, args, sigma, prm, d_in, d_syn, pool):
 
 
 def main():
+    t_start = time.perf_counter()
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    skipped = []
+
+    def time_left_for(leg, cost_s):
+        """Optional legs run only when the budget still covers their estimated cost (every rank decides alike: the
+        estimate is compared with rank 0's clock)."""
+        left = args.time_budget - (time.perf_counter() - t_start)
+        ok = left > cost_s
+        if world > 1:
+            t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+            dist.broadcast(t, src=0)
+            ok = bool(t.item() > 0.5)
+        if not ok:
+            skipped.append({"leg": leg, "estimated_s": cost_s, "time_left_s": left})
+        return ok
 
     import torch
     import torch.distributed as dist
@@ -486,6 +507,7 @@ def main():
     # e2e: the same call with HOST buffers (pageable numpy arrays, as a caller of the reference API has them): the
     # strided gather of prepare_vectors, H2D of channel values + syndromes, D2H of packed decisions all inside
     e2e = e2e_small = None
+    step_s = elapsed / args.steps
     if not args.skip_e2e:
         inp_host = d_in.cpu().numpy()
         h_res = np.zeros((n_frames, W), dtype=np.uint32)
@@ -513,8 +535,8 @@ def main():
                     "device_s_per_step": float(np.mean([r["device_s"] for r in hreps])),
                     "input_row_stride_bytes": pool * s}
 
-        e2e = e2e_leg(inp_host, syn_host, args.pool, args.steps)
-        if args.small_pool and args.small_pool < args.pool:
+        e2e = e2e_leg(inp_host, syn_host, args.pool, max(1, min(args.steps, args.e2e_steps)))
+        if args.small_pool and args.small_pool < args.pool and time_left_for("e2e_small_pool", 3.2 * step_s):
             sp = args.small_pool
             e2e_small = e2e_leg(np.ascontiguousarray(inp_host[:, :sp]), np.ascontiguousarray(syn_host[:sp]), sp,
                                 min(args.steps, 2))
@@ -523,7 +545,7 @@ def main():
     # one queue of world x n_frames frames shared by all ranks (one process per GPU, atomic cursor in POSIX shared
     # memory): dynamic load balance, no data-path collective; and the strong-scaling point (n_frames frames in total)
     shared = None
-    if world > 1 and not args.skip_extra:
+    if world > 1 and not args.skip_extra and time_left_for("shared_queue", 3.5 * step_s + 20):
         shared = {}
         name = "ldpc_b200_bench_%s" % os.environ.get("MASTER_PORT", "0")
         for label, n_total in (("weak", n_frames * world), ("strong", n_frames)):
@@ -561,7 +583,7 @@ def main():
     # EXTENSION, not the reference's end-of-input behaviour: frames retire when they stop once the
     # input is exhausted and the survivors are compacted -- reported beside the headline, never as the headline
     early = None
-    if not args.skip_extra and not args.early_retire:
+    if not args.skip_extra and not args.early_retire and time_left_for("extension_early_retire", 2.1 * step_s):
         def step_early():
             return dec.decode(L.AWGN, prm, d_in, d_syn, n_frames=n_frames, results=d_res, pool_frames=args.pool,
                               flags=L.FLAG_EARLY_RETIRE, **common)
@@ -580,18 +602,20 @@ def main():
     cpu = ref_cuda = others = None
     if rank == 0 and world == 1:
         if not args.skip_cpu:
-            cpu, _ = cpu_sample(args, gen)
+            cpu, _ = cpu_sample(args, gen)  # ~10-25 s: part of the contract, not optional
         if not args.skip_extra:
-            try:
-                ref_cuda = ref_cuda_build_leg(L, gen, args, sigma, prm, d_in, d_syn, args.pool)
-            except Exception as e:  # a baseline leg must never take the headline line down
-                ref_cuda = {"unavailable": repr(e)}
+            if time_left_for("ref_cuda_build", 45):
+                try:
+                    ref_cuda = ref_cuda_build_leg(L, gen, args, sigma, prm, d_in, d_syn, args.pool)
+                except Exception as e:  # a baseline leg must never take the headline line down
+                    ref_cuda = {"unavailable": repr(e)}
             del dec, d_in, d_syn, d_ref, d_res
             torch.cuda.empty_cache()
-            try:
-                others = other_configs_leg(L, peak, peak_kind)
-            except Exception as e:
-                others = {"unavailable": repr(e)}
+            if time_left_for("other_configs", 75):
+                try:
+                    others = other_configs_leg(L, peak, peak_kind)
+                except Exception as e:
+                    others = {"unavailable": repr(e)}
 
     if rank == 0:
         line = {
@@ -612,7 +636,8 @@ def main():
             "syndromes_satisfied": ok, "frac_converged": float(conv.mean()),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_small_pool": e2e_small,
             "ref_cuda_build": ref_cuda, "other_configs": others, "shared_queue": shared, "extension_early_retire": early,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "skipped_legs": skipped,
+            "wall_s": time.perf_counter() - t_start,
         }
         line["value_over_roofline"] = line["value"] / line["roofline_mbps"]
         print(json.dumps(line), flush=True)
