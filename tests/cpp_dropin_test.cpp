@@ -9,6 +9,17 @@
 
 using namespace ldpc_b200;
 
+// a channel the decoder has no conversion kernel for (decoding_input_is_llr() == true): the class converts the channel
+// values with llr() on the host, as the reference's prepare_vectors does (ldpc_decoder_gpu.cu:209-215)
+class custom_channel : public noisy_channel {
+  float m_factor;
+
+public:
+  explicit custom_channel(float sigma) : m_factor(2 * (1 / (sigma * sigma))) {} // as biawgn_channel::factor()
+  float llr(const float val) const override { return m_factor * val; }
+  channelType channel() const override { return groupGauss; }
+};
+
 int main(int argc, char **argv) {
   if (argc < 2) return 2;
   try {
@@ -53,6 +64,17 @@ int main(int argc, char **argv) {
                   (unsigned long long)report2.device_report.frames_decoded, (unsigned long long)errors2, report2.max_iter,
                   report2.min_iter, report2.avg_iter);
       if (errors2 != 0 || report2.device_report.frames_decoded != n) return 6;
+    }
+    // a custom channel: same LLRs as the AWGN channel, computed by channel.llr() on the host
+    {
+      custom_channel custom(sigma);
+      ldpc_decoder_gpu dec3(code, custom, sp);
+      if (!dec3.decoding_input_is_llr()) return 7;
+      std::vector<uint32_t> res3(res.size(), 0u);
+      test_report report3;
+      dec3.decode(dp, n, input.data(), syn.data(), res3.data(), report3, 1);
+      if (res3 != res || report3.max_iter != report.max_iter || report3.min_iter != report.min_iter) return 8;
+      std::printf("custom channel: identical to the AWGN decode\n");
     }
     // malformed input must surface as the reference's exception type
     try {

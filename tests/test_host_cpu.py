@@ -251,3 +251,38 @@ def test_locality_storage_order_recovers_hidden_locality():
 
     before, after = mean_span(np.arange(m)), mean_span(co.astype(np.int64))
     assert after < before / 20, (before, after)
+
+
+def test_dropin_half_conversions_match_numpy(tmp_path):
+    """include/ldpc_b200_dropin.hpp converts halves on the host for channels without a device kernel (C++14 has no half
+    type): float -> half rounds to nearest even exactly like numpy, incl. subnormals, ties, overflow, infinities and NaN;
+    half -> float is exact for all 65536 patterns."""
+    import subprocess
+
+    exe = str(tmp_path / "cpp_half_test")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(ROOT, "tests", "cpp_half_test.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "ldpc_decoder_b200"), "-lldpc_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "ldpc_decoder_b200")])
+    rng = np.random.default_rng(3)
+    halves = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
+    ties = (halves[:-1].astype(np.float64) + halves[1:].astype(np.float64)) / 2           # exact midpoints of neighbours
+    vals = np.concatenate([
+        np.exp(rng.uniform(np.log(1e-9), np.log(1e6), 200000)).astype(np.float32) * rng.choice([-1, 1], 200000).astype(np.float32),
+        ties[np.isfinite(ties)].astype(np.float32),
+        halves[np.isfinite(halves)],
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 65504.0, 65519.99, 65520.0, 1e-8, 5.96e-8, 2.98e-8, 2.9802322e-8],
+                 dtype=np.float32)])
+    src, dst = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    vals.tofile(src)
+    subprocess.check_call([exe, src, dst])
+    raw = np.fromfile(dst, dtype=np.uint8)
+    got = raw[: 2 * vals.size].view(np.uint16)
+    with np.errstate(over="ignore"):
+        want = vals.astype(np.float16).view(np.uint16)
+    nan = np.isnan(vals)
+    assert np.array_equal(got[~nan], want[~nan])
+    assert np.all((got[nan] & 0x7C00) == 0x7C00) and np.all(got[nan] & 0x3FF)
+    back = raw[2 * vals.size:].view(np.float32)
+    ok = ~np.isnan(halves)
+    assert np.array_equal(back[ok].view(np.uint32), halves[ok].view(np.uint32)) and np.all(np.isnan(back[~ok]))
