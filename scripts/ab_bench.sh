@@ -7,7 +7,7 @@ for spec in "$@"; do
   lib=${spec%%:*}; envs=${spec#*:}
   name=$(echo "${lib%.so}_${envs}" | tr ' =' '__')
   echo "### $lib $envs"
-  env LDPC_B200_LIB=ab/$lib $envs python bench.py --steps 1 --warmup 1 --skip-e2e --skip-cpu > gpurun_out/${TAG}_${name}.log 2>&1
+  env LDPC_B200_LIB=ab/$lib $envs python bench.py --steps 1 --warmup 1 --skip-e2e --skip-cpu --skip-extra > gpurun_out/${TAG}_${name}.log 2>&1
   tail -1 gpurun_out/${TAG}_${name}.log | python -c "
 import sys,json
 try:
