@@ -288,13 +288,13 @@ struct ldpc_b200_decoder {
     if (!h_stage_syn.p || h_stage_syn.n < need) CU_TRY(h_stage_syn.alloc(need));
     return LDPC_B200_OK;
   }
-  // EXPERIMENT, off by default (LDPC_B200_STAGE_SLACK_PCT > 0): stage host frames in passes of a few thousand frames
-  // instead of one pass per check period -- the ring then holds frames_in_flight + slack frames, a pass starts when
-  // fewer than a quarter of the slack is staged beyond what the next check may need, and fills the slack, so it reads
-  // kilobyte runs of every row of the caller's strided array instead of the ~900 bytes one period consumes.  Measured
-  // (scripts/e2e_feed.sh, 4096 distinct frames, 4 host threads): 15.06 s per e2e step with 50 % slack against 14.89 s
-  // without (2 threads: 16.04 vs 15.34 s): the big passes are bursts the flood iterations of ONE period cannot hide.
-  uint32_t stage_slack_pct = 0;
+  // Look-ahead slack of the staging ring of host-fed calls (LDPC_B200_STAGE_SLACK_PCT, % of the frames in flight): the
+  // ring holds frames_in_flight + slack frames, so the frames the NEXT check may load are normally staged a period in
+  // advance and the host thread can enqueue the next period's kernels first and gather afterwards -- the strided
+  // gather (27 ms per period alone on a host, ~90 ms with peaks above a period when 8 ranks share one,
+  // profiles/r06_bench_8gpu_feed.json) leaves the critical path of the launches.  (A first version that kept the gather
+  // before the launches and merely made its passes bigger was slower: profiles/README.md.)
+  uint32_t stage_slack_pct = 25;
   uint32_t stage_slack(uint32_t batch, uint32_t ring_block) const {
     return uint32_t(uint64_t(batch) * stage_slack_pct / 100) / ring_block * ring_block;
   }
@@ -1649,11 +1649,11 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
     // frames the next refill may need: at most B beyond what has been loaded so far
     if (lq) lq->reserve_upto(uint64_t(next_known) + queue_ahead);
     {
-      // the next check may load up to B frames beyond next_known: they must be staged before it runs.  With slack, a
-      // pass starts while a quarter of the slack is still staged beyond that, and fills the slack.
-      const uint64_t need = uint64_t(next_known) + B;
-      if (!slack || uint64_t(feed.staged) < std::min<uint64_t>(n_frames, need + slack / 4))
-        st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, need + slack)));
+      // The next check may load up to B frames beyond next_known: they must be staged before it is enqueued.  With a
+      // look-ahead slack in the ring this is normally already the case (the top-up below ran a period ago), so the
+      // host enqueues the next period at once and gathers AFTERWARDS, while the device works through it.
+      const uint64_t need = std::min<uint64_t>(n_frames, uint64_t(next_known) + B);
+      if (uint64_t(feed.staged) < need) st = stage_upto(uint32_t(need));
       if (st != LDPC_B200_OK) return st;
     }
     // service of this period + the next period's flood iterations (run ahead: no-ops once the scheduler has
@@ -1698,6 +1698,10 @@ static ldpc_b200_status decode_impl(ldpc_b200_decoder *d, const ldpc_b200_decode
       enqueue_iterations(period + 1);
     }
     CU_TRY(cudaGetLastError());
+    if (slack) { // top the ring up for the checks after this one: off the critical path of the launches above
+      st = stage_upto(uint32_t(std::min<uint64_t>(n_frames, uint64_t(next_known) + B + slack)));
+      if (st != LDPC_B200_OK) return st;
+    }
     ++period;
     if (period > period_limit) return fail(LDPC_B200_ERR_INVALID, "scheduler made no progress (internal error)");
   }
