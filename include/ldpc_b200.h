@@ -4,8 +4,11 @@
  * This is the drop-in boundary for the reference's decoder class
  *   h/ldpc_decoder_gpu.h:15-139  (CUDA twin h/ldpc_decoder_gpu_cuda.h:11-145)
  * of kunzjacq/ldpc_decoder.  The reference has no FFI layer of its own; the
- * header-compatible C++14 class in ldpc_decoder_b200/csrc/ldpc_decoder_gpu.h
- * forwards to these entry points.
+ * header-compatible C++14 class (ldpc_b200_dropin.hpp, instantiated in the global
+ * namespace by ldpc_decoder_gpu.h / ldpc_decoder_gpu_cuda.h of this directory for the
+ * reference tree's own types, and in namespace ldpc_b200 by
+ * ldpc_decoder_b200/csrc/ldpc_decoder_gpu.h) forwards to these entry points (see
+ * INTEGRATION.md).
  *
  * Plain pointers and sizes only; no exceptions cross this boundary: every
  * function returns an ldpc_b200_status and ldpc_b200_last_error() gives text.
