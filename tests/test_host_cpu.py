@@ -286,3 +286,20 @@ def test_dropin_half_conversions_match_numpy(tmp_path):
     back = raw[2 * vals.size:].view(np.float32)
     ok = ~np.isnan(halves)
     assert np.array_equal(back[ok].view(np.uint32), halves[ok].view(np.uint32)) and np.all(np.isnan(back[~ok]))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (absent on the GPU box)")
+def test_reference_main_cpp_compiles_and_links_against_the_dropin_header():
+    """Build-only half of the drop-in claim (the GPU half is test_reference_main_cpp_builds_and_runs_against_the_dropin_header):
+    the reference's own src/main.cpp and harness sources, unchanged, compile with include/ of this repository first on
+    the include path and link with libldpc_b200.so (oracle/Makefile refdropin); the program starts and prints the
+    reference's usage text without a device."""
+    import subprocess
+
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "refdropin"])
+    for prec in ("fp16", "fp32"):
+        exe = os.path.join(ROOT, "oracle", "_ref", f"dropin_ldpc_decoder_{prec}")
+        r = subprocess.run([exe, "-h"], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and "-f s where s is the name of the code file" in r.stdout
+        ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+        assert "libldpc_b200.so" in ldd and "libcudart" not in ldd.split("libldpc_b200.so")[0]
